@@ -1,0 +1,111 @@
+// common.cuh — shared host/device helpers for the dgll_b200 C-ABI library.
+// sm_100a only (B200).  No torch types anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/dgll_b200.h"
+
+namespace dgllb {
+
+// ---------------------------------------------------------------- errors --
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launch_count;
+
+struct DevInfo {
+    int sm_count;
+    int cc_major, cc_minor;
+    long long l2_bytes;
+    int max_smem_optin;
+};
+// Cached properties of the current device (thread-safe, per device index).
+int get_devinfo(DevInfo* out);
+
+#define DGLLB_CUDA_TRY(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            dgllb::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,   \
+                             cudaGetErrorString(_e));                               \
+            return DGLLB_ERR_CUDA;                                                  \
+        }                                                                           \
+    } while (0)
+
+#define DGLLB_REQUIRE(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            dgllb::set_error(__VA_ARGS__);       \
+            return DGLLB_ERR_INVALID;            \
+        }                                        \
+    } while (0)
+
+// call after every kernel launch
+#define DGLLB_LAUNCH_CHECK()                                                        \
+    do {                                                                            \
+        dgllb::g_launch_count.fetch_add(1, std::memory_order_relaxed);              \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) {                                                    \
+            dgllb::set_error("kernel launch failed at %s:%d: %s", __FILE__,         \
+                             __LINE__, cudaGetErrorString(_e));                     \
+            return DGLLB_ERR_CUDA;                                                  \
+        }                                                                           \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------ device helpers ----
+#ifdef __CUDACC__
+
+// 128-bit streaming load through the read-only path, no L1 allocation: feature
+// rows are reused at L2 (several destinations share a source) but not in L1.
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_nc_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_cs_f4(float* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <typename RP>
+__device__ __forceinline__ long long ld_rowptr(const RP* p, long long i) {
+    return static_cast<long long>(p[i]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dgllb

@@ -1,0 +1,475 @@
+// gat.cu — fused SDDMM + edge-softmax + aggregation for multi-head GAT (sm_100a).
+//
+// Replaces sparseGatConv.forward (dgll/nn/Convolution/gatconv.py:111-148: edge
+// gather+cat, exp(-leakyrelu), two COO SpMMs, divide) and the dense N^2 masked
+// softmax of gatConv.forward (:30-54), plus their autograd (SpecialSpmmFunction
+// backward :71-81, which materialises a dense N x N product).
+//
+// GAT's attention logit is additive: z_ij = lrelu(a_l.Wh_i + a_r.Wh_j) = lrelu(el_i + er_j),
+// so the SDDMM collapses to two per-node scalars per head (computed by the dense
+// transform's caller) and the whole layer is ONE pass over the edges:
+//   work item = (dst row, head, slab of the head's D columns); a group of LANES
+//   lanes walks the row's edges LANES at a time: each lane scores one edge
+//   (gathers er_j), the group does an online-softmax update (running max m,
+//   running sum l, accumulator rescale), then the chunk's source rows stream
+//   through with 128-bit loads, 8 in flight per lane.  No [E] tensor is written.
+// Backward (deterministic, no atomics): pass 1 over the CSR recomputes alpha,
+// forms dalpha = <g_i, Wh_j> (the SDDMM) and writes dz per edge; pass 2 over the
+// transposed CSR accumulates d_Wh_j = sum_i alpha_ij g_i and d_er_j.
+// Algorithmic bytes fwd: nnz*(4 + F*4 + heads*4) + n_dst*(F*4 + heads*4 + r).
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace dgllb {
+
+struct GatParams {
+    const void* row_ptr;
+    int rp64;
+    const int* col;
+    const float* Wh;
+    long long ldw;
+    const float* el;
+    const float* er;
+    long long ld_e;
+    float* out;
+    long long ldo;
+    float* row_max;
+    float* row_sum;
+    long long n_dst;
+    int heads;
+    int D;
+    int n_slabs;
+    float slope;
+    float sign;  // +1 softmax(lrelu), -1 exp(-lrelu)/sum
+    int epi;
+};
+
+__device__ __forceinline__ long long gat_rp(const void* p, int is64, long long i) {
+    return is64 ? reinterpret_cast<const long long*>(p)[i]
+                : static_cast<long long>(reinterpret_cast<const int*>(p)[i]);
+}
+
+template <int LANES>
+__device__ __forceinline__ float group_max(float v, unsigned gmask) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, o, LANES));
+    return v;
+}
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v, unsigned gmask) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, LANES);
+    return v;
+}
+
+constexpr int kGatThreads = 256;
+constexpr int kGatUnroll = 8;
+
+template <int VE, int LANES>
+__global__ void __launch_bounds__(kGatThreads)
+gat_forward_kernel(const GatParams p) {
+    const int lig = threadIdx.x & (LANES - 1);
+    const long long group = (static_cast<long long>(blockIdx.x) * kGatThreads + threadIdx.x) / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu
+                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
+    const int per_row = p.heads * p.n_slabs;
+    const long long row = group / per_row;
+    if (row >= p.n_dst) return;
+    const int rem = static_cast<int>(group - row * per_row);
+    const int head = rem / p.n_slabs;
+    const int slab = rem - head * p.n_slabs;
+    const long long beg = gat_rp(p.row_ptr, p.rp64, row), end = gat_rp(p.row_ptr, p.rp64, row + 1);
+
+    const int dcol = (slab * LANES + lig) * VE;  // column inside the head
+    const bool lane_on = dcol < p.D;
+    const int col0 = head * p.D + dcol;
+    const float* __restrict__ Wb = p.Wh + col0;
+    const float el_i = __ldg(p.el + row * p.ld_e + head);
+
+    float m = -INFINITY, l = 0.f;
+    float acc[VE];
+#pragma unroll
+    for (int a = 0; a < VE; ++a) acc[a] = 0.f;
+
+    for (long long e0 = beg; e0 < end; e0 += LANES) {
+        const int n = static_cast<int>(min(static_cast<long long>(LANES), end - e0));
+        int my_c = 0;
+        float my_s = -INFINITY;
+        if (lig < n) {
+            my_c = __ldg(p.col + e0 + lig);
+            float z = el_i + __ldg(p.er + static_cast<long long>(my_c) * p.ld_e + head);
+            z = z > 0.f ? z : p.slope * z;
+            my_s = p.sign * z;
+        }
+        const float mc = group_max<LANES>(my_s, gmask);
+        const float m_new = fmaxf(m, mc);
+        const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
+        const float my_p = (lig < n) ? expf(my_s - m_new) : 0.f;
+        l = l * corr + group_sum<LANES>(my_p, gmask);
+        m = m_new;
+#pragma unroll
+        for (int a = 0; a < VE; ++a) acc[a] *= corr;
+
+        for (int k = 0; k < n; k += kGatUnroll) {
+            float4 raw[kGatUnroll];
+            float w[kGatUnroll];
+#pragma unroll
+            for (int u = 0; u < kGatUnroll; ++u) {
+                const int src = (k + u) & (LANES - 1);
+                const long long c = __shfl_sync(gmask, my_c, src, LANES);
+                w[u] = __shfl_sync(gmask, my_p, src, LANES);
+                if (k + u < n && lane_on) {
+                    if (VE == 4) raw[u] = ldg_nc_f4(Wb + c * p.ldw);
+                    else raw[u].x = ldg_nc_f1(Wb + c * p.ldw);
+                } else {
+                    raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    w[u] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kGatUnroll; ++u) {
+                acc[0] = fmaf(w[u], raw[u].x, acc[0]);
+                if (VE == 4) {
+                    acc[1] = fmaf(w[u], raw[u].y, acc[1]);
+                    acc[2] = fmaf(w[u], raw[u].z, acc[2]);
+                    acc[3] = fmaf(w[u], raw[u].w, acc[3]);
+                }
+            }
+        }
+    }
+
+    if (slab == 0 && lig == 0) {
+        if (p.row_max) p.row_max[row * p.heads + head] = m;
+        if (p.row_sum) p.row_sum[row * p.heads + head] = l;
+    }
+    if (!lane_on) return;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    float* __restrict__ o = p.out + row * p.ldo + col0;
+    const int valid = min(VE, p.D - dcol);
+#pragma unroll
+    for (int a = 0; a < VE; ++a) {
+        float v = acc[a] * inv;
+        if (p.epi & DGLLB_EPI_RELU) v = fmaxf(v, 0.f);
+        if (p.epi & DGLLB_EPI_ELU) v = v > 0.f ? v : expm1f(v);
+        acc[a] = v;
+    }
+    if (VE == 4 && valid == 4) {
+        stg_cs_f4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    } else {
+#pragma unroll
+        for (int a = 0; a < VE; ++a)
+            if (a < valid) o[a] = acc[a];
+    }
+}
+
+
+// ------------------------------------------------------------- backward --
+struct GatBwdParams {
+    const void* row_ptr;
+    int rp64;
+    const int* col;
+    const void* t_row_ptr;
+    const int* t_col;
+    const int* perm;
+    const float* Wh;
+    long long ldw;
+    const float* el;
+    const float* er;
+    long long ld_e;
+    const float* out;
+    long long ldo;
+    const float* row_max;
+    const float* row_sum;
+    const float* g;
+    long long ldg;
+    float* d_Wh;
+    long long ldd;
+    float* d_el;
+    float* d_er;
+    long long ld_de;
+    float2* ws;  // (alpha, dz) per (edge, head)
+    long long n_dst;
+    long long n_src;
+    int heads;
+    int D;
+    float slope;
+    float sign;
+};
+
+// Pass 1: group = (dst row i, head).  Lane columns: chunk k covers (k*LANES + lig)*VE.
+template <int VE, int LANES, int NCH>
+__global__ void __launch_bounds__(kGatThreads)
+gat_backward_edge_kernel(const GatBwdParams p) {
+    const int lig = threadIdx.x & (LANES - 1);
+    const long long group = (static_cast<long long>(blockIdx.x) * kGatThreads + threadIdx.x) / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu
+                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
+    const long long row = group / p.heads;
+    if (row >= p.n_dst) return;
+    const int head = static_cast<int>(group - row * p.heads);
+    const long long beg = gat_rp(p.row_ptr, p.rp64, row), end = gat_rp(p.row_ptr, p.rp64, row + 1);
+
+    float gi[NCH][VE];
+    float c_part = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int dcol = (k * LANES + lig) * VE;
+#pragma unroll
+        for (int a = 0; a < VE; ++a) {
+            float gv = 0.f, ov = 0.f;
+            if (dcol + a < p.D) {
+                gv = __ldg(p.g + row * p.ldg + head * p.D + dcol + a);
+                ov = __ldg(p.out + row * p.ldo + head * p.D + dcol + a);
+            }
+            gi[k][a] = gv;
+            c_part = fmaf(gv, ov, c_part);
+        }
+    }
+    const float c_i = group_sum<LANES>(c_part, gmask);  // sum_k alpha_ik dalpha_ik = <g_i, out_i>
+    const float el_i = __ldg(p.el + row * p.ld_e + head);
+    const float m_i = __ldg(p.row_max + row * p.heads + head);
+    const float l_i = __ldg(p.row_sum + row * p.heads + head);
+    const float inv_l = l_i > 0.f ? 1.f / l_i : 0.f;
+    float del_acc = 0.f;
+
+    for (long long e0 = beg; e0 < end; e0 += LANES) {
+        const int n = static_cast<int>(min(static_cast<long long>(LANES), end - e0));
+        int my_c = 0;
+        float my_alpha = 0.f, my_dact = 0.f;
+        if (lig < n) {
+            my_c = __ldg(p.col + e0 + lig);
+            const float z = el_i + __ldg(p.er + static_cast<long long>(my_c) * p.ld_e + head);
+            const float lz = z > 0.f ? z : p.slope * z;
+            my_alpha = expf(p.sign * lz - m_i) * inv_l;
+            my_dact = p.sign * (z > 0.f ? 1.f : p.slope);
+        }
+        float my_dalpha = 0.f;
+        for (int k0 = 0; k0 < n; ++k0) {
+            const long long c = __shfl_sync(gmask, my_c, k0, LANES);
+            float part = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int dcol = (k * LANES + lig) * VE;
+                if (dcol < p.D) {
+                    const float* w = p.Wh + c * p.ldw + head * p.D + dcol;
+                    if (VE == 4) {
+                        const float4 v = ldg_nc_f4(w);
+                        part = fmaf(gi[k][0], v.x, part);
+                        part = fmaf(gi[k][1 % VE], v.y, part);
+                        part = fmaf(gi[k][2 % VE], v.z, part);
+                        part = fmaf(gi[k][3 % VE], v.w, part);
+                    } else {
+                        part = fmaf(gi[k][0], ldg_nc_f1(w), part);
+                    }
+                }
+            }
+            const float dot = group_sum<LANES>(part, gmask);
+            if (lig == k0) my_dalpha = dot;
+        }
+        if (lig < n) {
+            const float dz = my_alpha * (my_dalpha - c_i) * my_dact;
+            p.ws[(e0 + lig) * p.heads + head] = make_float2(my_alpha, dz);
+            del_acc += dz;
+        }
+    }
+    const float del = group_sum<LANES>(del_acc, gmask);
+    if (lig == 0) p.d_el[row * p.ld_de + head] = del;
+}
+
+// Pass 2: group = (src row j, head, slab) over the transposed CSR.
+template <int VE, int LANES>
+__global__ void __launch_bounds__(kGatThreads)
+gat_backward_node_kernel(const GatBwdParams p, int n_slabs) {
+    const int lig = threadIdx.x & (LANES - 1);
+    const long long group = (static_cast<long long>(blockIdx.x) * kGatThreads + threadIdx.x) / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu
+                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
+    const int per_row = p.heads * n_slabs;
+    const long long row = group / per_row;
+    if (row >= p.n_src) return;
+    const int rem = static_cast<int>(group - row * per_row);
+    const int head = rem / n_slabs;
+    const int slab = rem - head * n_slabs;
+    const long long beg = gat_rp(p.t_row_ptr, p.rp64, row), end = gat_rp(p.t_row_ptr, p.rp64, row + 1);
+    const int dcol = (slab * LANES + lig) * VE;
+    const bool lane_on = dcol < p.D;
+    const float* __restrict__ gb = p.g + head * p.D + dcol;
+
+    float acc[VE];
+#pragma unroll
+    for (int a = 0; a < VE; ++a) acc[a] = 0.f;
+    float der_acc = 0.f;
+
+    for (long long e0 = beg; e0 < end; e0 += LANES) {
+        const int n = static_cast<int>(min(static_cast<long long>(LANES), end - e0));
+        int my_i = 0;
+        float my_alpha = 0.f;
+        if (lig < n) {
+            my_i = __ldg(p.t_col + e0 + lig);
+            const long long eo = __ldg(p.perm + e0 + lig);
+            const float2 ad = __ldg(p.ws + eo * p.heads + head);
+            my_alpha = ad.x;
+            der_acc += ad.y;
+        }
+        for (int k = 0; k < n; k += kGatUnroll) {
+            float4 raw[kGatUnroll];
+            float w[kGatUnroll];
+#pragma unroll
+            for (int u = 0; u < kGatUnroll; ++u) {
+                const int src = (k + u) & (LANES - 1);
+                const long long i = __shfl_sync(gmask, my_i, src, LANES);
+                w[u] = __shfl_sync(gmask, my_alpha, src, LANES);
+                if (k + u < n && lane_on) {
+                    if (VE == 4) raw[u] = ldg_nc_f4(gb + i * p.ldg);
+                    else raw[u].x = ldg_nc_f1(gb + i * p.ldg);
+                } else {
+                    raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    w[u] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kGatUnroll; ++u) {
+                acc[0] = fmaf(w[u], raw[u].x, acc[0]);
+                if (VE == 4) {
+                    acc[1] = fmaf(w[u], raw[u].y, acc[1]);
+                    acc[2] = fmaf(w[u], raw[u].z, acc[2]);
+                    acc[3] = fmaf(w[u], raw[u].w, acc[3]);
+                }
+            }
+        }
+    }
+    if (slab == 0) {
+        const float der = group_sum<LANES>(der_acc, gmask);
+        if (lig == 0) p.d_er[row * p.ld_de + head] = der;
+    }
+    if (!lane_on) return;
+    float* __restrict__ o = p.d_Wh + row * p.ldd + head * p.D + dcol;
+    const int valid = min(VE, p.D - dcol);
+    if (VE == 4 && valid == 4) {
+        stg_cs_f4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    } else {
+#pragma unroll
+        for (int a = 0; a < VE; ++a)
+            if (a < valid) o[a] = acc[a];
+    }
+}
+
+template <int VE, int LANES>
+static int launch_gat_bwd_edge(const GatBwdParams& p, int nch, cudaStream_t st) {
+    const long long groups = p.n_dst * p.heads;
+    const int gpb = kGatThreads / LANES;
+    const long long blocks = (groups + gpb - 1) / gpb;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
+    const unsigned g = static_cast<unsigned>(blocks);
+    if (nch <= 1) gat_backward_edge_kernel<VE, LANES, 1><<<g, kGatThreads, 0, st>>>(p);
+    else if (nch <= 2) gat_backward_edge_kernel<VE, LANES, 2><<<g, kGatThreads, 0, st>>>(p);
+    else if (nch <= 4) gat_backward_edge_kernel<VE, LANES, 4><<<g, kGatThreads, 0, st>>>(p);
+    else {
+        set_error("gat_backward: head width D=%d too large for this build", p.D);
+        return DGLLB_ERR_UNSUPPORTED;
+    }
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+template <int VE>
+static int launch_gat_bwd(const GatBwdParams& p, cudaStream_t st) {
+    int lanes = 32;
+    if (VE > 1 && p.D <= 8 * VE) lanes = 8;
+    else if (VE > 1 && p.D <= 16 * VE) lanes = 16;
+    const int nch = (p.D + lanes * VE - 1) / (lanes * VE);
+    int rc;
+    if (p.n_dst > 0) {
+        if (lanes == 8) rc = launch_gat_bwd_edge<VE, 8>(p, nch, st);
+        else if (lanes == 16) rc = launch_gat_bwd_edge<VE, 16>(p, nch, st);
+        else rc = launch_gat_bwd_edge<VE, 32>(p, nch, st);
+        if (rc != DGLLB_OK) return rc;
+    }
+    if (p.n_src > 0) {
+        const long long groups = p.n_src * p.heads * nch;
+        const int gpb = kGatThreads / lanes;
+        const long long blocks = (groups + gpb - 1) / gpb;
+        DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
+        const unsigned g = static_cast<unsigned>(blocks);
+        if (lanes == 8) gat_backward_node_kernel<VE, 8><<<g, kGatThreads, 0, st>>>(p, nch);
+        else if (lanes == 16) gat_backward_node_kernel<VE, 16><<<g, kGatThreads, 0, st>>>(p, nch);
+        else gat_backward_node_kernel<VE, 32><<<g, kGatThreads, 0, st>>>(p, nch);
+        DGLLB_LAUNCH_CHECK();
+    }
+    return DGLLB_OK;
+}
+
+template <int VE>
+static int launch_gat_fwd(GatParams& p, cudaStream_t st) {
+    int lanes = 32;
+    if (VE > 1 && p.D <= 8 * VE) lanes = 8;
+    else if (VE > 1 && p.D <= 16 * VE) lanes = 16;
+    p.n_slabs = (p.D + lanes * VE - 1) / (lanes * VE);
+    const long long groups = p.n_dst * p.heads * p.n_slabs;
+    const int gpb = kGatThreads / lanes;
+    const long long blocks = (groups + gpb - 1) / gpb;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "gat_forward: grid too large");
+    const unsigned g = static_cast<unsigned>(blocks);
+    if (lanes == 8) gat_forward_kernel<VE, 8><<<g, kGatThreads, 0, st>>>(p);
+    else if (lanes == 16) gat_forward_kernel<VE, 16><<<g, kGatThreads, 0, st>>>(p);
+    else gat_forward_kernel<VE, 32><<<g, kGatThreads, 0, st>>>(p);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+}  // namespace dgllb
+
+using namespace dgllb;
+
+extern "C" int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                                 const float* Wh, int64_t ldw, const float* el, const float* er,
+                                 int64_t ld_e, float* out, int64_t ldo, float* row_max, float* row_sum,
+                                 int64_t n_dst, int64_t n_src, int heads, int D, float slope,
+                                 int mode, int epilogue, void* stream) {
+    DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && heads >= 1 && D >= 1, "gat_forward: bad sizes");
+    if (n_dst == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(row_ptr && Wh && el && er && out, "gat_forward: null pointer");
+    DGLLB_REQUIRE(ldw >= static_cast<int64_t>(heads) * D && ldo >= static_cast<int64_t>(heads) * D,
+                  "gat_forward: leading dimension smaller than heads*D");
+    DGLLB_REQUIRE(ld_e >= heads, "gat_forward: ld_e smaller than heads");
+    DGLLB_REQUIRE(mode == DGLLB_GAT_SOFTMAX || mode == DGLLB_GAT_EXP_NEG, "gat_forward: unknown mode %d", mode);
+    GatParams p;
+    p.row_ptr = row_ptr; p.rp64 = row_ptr_is64; p.col = col_idx; p.Wh = Wh; p.ldw = ldw;
+    p.el = el; p.er = er; p.ld_e = ld_e; p.out = out; p.ldo = ldo; p.row_max = row_max; p.row_sum = row_sum;
+    p.n_dst = n_dst; p.heads = heads; p.D = D; p.n_slabs = 1; p.slope = slope;
+    p.sign = mode == DGLLB_GAT_SOFTMAX ? 1.f : -1.f;
+    p.epi = epilogue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = aligned16(Wh) && aligned16(out) && ldw % 4 == 0 && ldo % 4 == 0 && D % 4 == 0;
+    return vec ? launch_gat_fwd<4>(p, st) : launch_gat_fwd<1>(p, st);
+}
+
+extern "C" int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                                  const void* t_row_ptr, const int32_t* t_col_idx, const int32_t* perm,
+                                  const float* Wh, int64_t ldw, const float* el, const float* er,
+                                  int64_t ld_e, const float* out, int64_t ldo, const float* row_max,
+                                  const float* row_sum, const float* g, int64_t ldg, float* d_Wh,
+                                  int64_t ldd, float* d_el, float* d_er, int64_t ld_de, float* edge_ws,
+                                  int64_t n_dst, int64_t n_src, int heads, int D, float slope,
+                                  int mode, void* stream) {
+    DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && heads >= 1 && D >= 1, "gat_backward: bad sizes");
+    if (n_dst == 0 && n_src == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(row_ptr && t_row_ptr && Wh && el && er && out && row_max && row_sum && g && d_Wh && d_el &&
+                      d_er && edge_ws,
+                  "gat_backward: null pointer");
+    DGLLB_REQUIRE(mode == DGLLB_GAT_SOFTMAX || mode == DGLLB_GAT_EXP_NEG, "gat_backward: unknown mode %d", mode);
+    const int64_t FD = static_cast<int64_t>(heads) * D;
+    DGLLB_REQUIRE(ldw >= FD && ldo >= FD && ldg >= FD && ldd >= FD && ld_e >= heads && ld_de >= heads,
+                  "gat_backward: leading dimension too small");
+    GatBwdParams p;
+    p.row_ptr = row_ptr; p.rp64 = row_ptr_is64; p.col = col_idx; p.t_row_ptr = t_row_ptr; p.t_col = t_col_idx;
+    p.perm = perm; p.Wh = Wh; p.ldw = ldw; p.el = el; p.er = er; p.ld_e = ld_e; p.out = out; p.ldo = ldo;
+    p.row_max = row_max; p.row_sum = row_sum; p.g = g; p.ldg = ldg; p.d_Wh = d_Wh; p.ldd = ldd;
+    p.d_el = d_el; p.d_er = d_er; p.ld_de = ld_de; p.ws = reinterpret_cast<float2*>(edge_ws);
+    p.n_dst = n_dst; p.n_src = n_src; p.heads = heads; p.D = D; p.slope = slope;
+    p.sign = mode == DGLLB_GAT_SOFTMAX ? 1.f : -1.f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = aligned16(Wh) && aligned16(g) && aligned16(d_Wh) && ldw % 4 == 0 && ldg % 4 == 0 &&
+                     ldd % 4 == 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(edge_ws) & 7) == 0;
+    return vec ? launch_gat_bwd<4>(p, st) : launch_gat_bwd<1>(p, st);
+}

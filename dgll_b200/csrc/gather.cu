@@ -1,0 +1,253 @@
+// gather.cu — sampled-block feature gather for sm_100a.
+//
+// Replaces: features[nodes] (dgll/data/dgraph.py:105), the HBM-cache gather and
+// masked scatter of GraphCacheServer.fetch_data / fetch_from_cache
+// (dgll/FeatureCache/storage.py:151-210).
+//
+// Design: a row gather is a pure byte move, so rows travel as TMA bulk copies
+// (cp.async.bulk global->shared with an mbarrier transaction count, then
+// cp.async.bulk shared->global) — no registers, one elected lane per warp
+// drives a ring of kSlots shared-memory slots, so every warp keeps kSlots row
+// pieces in flight.  SASS: UBLKCP.  Rows whose base/stride are not 16-byte
+// multiples fall back to a vector/scalar LDG copy.
+// Algorithmic bytes: M * (id_bytes + 2 * row_bytes).
+#include "common.cuh"
+
+namespace dgllb {
+
+constexpr int kGatherWarps = 8;      // warps per CTA
+constexpr int kSlots = 4;            // ring depth per warp
+constexpr int kSlotBytes = 4096;     // piece size (rows longer than this are split)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+struct GatherSrc {
+    // resolves the source address of output row i
+    const char* table;
+    long long stride;
+    const void* ids;
+    int ids64;
+    // optional cache split (GraphCacheServer): when gpu_flag != nullptr
+    const unsigned char* gpu_flag;
+    const long long* local2cache;
+    const long long* nid_map;
+    const char* host_table;
+    long long host_stride;
+};
+
+__device__ __forceinline__ const char* resolve_row(const GatherSrc& s, long long i, bool* is_host) {
+    const long long id = s.ids64 ? reinterpret_cast<const long long*>(s.ids)[i]
+                                 : static_cast<long long>(reinterpret_cast<const int*>(s.ids)[i]);
+    *is_host = false;
+    if (s.gpu_flag) {
+        if (s.gpu_flag[id]) return s.table + s.local2cache[id] * s.stride;
+        *is_host = true;
+        const long long hid = s.nid_map ? s.nid_map[id] : id;
+        return s.host_table + hid * s.host_stride;
+    }
+    return s.table + id * s.stride;
+}
+
+// TMA bulk-copy gather.  grid = persistent CTAs, each warp strides over pieces.
+__global__ void __launch_bounds__(kGatherWarps * 32)
+gather_bulk_kernel(const GatherSrc src, char* __restrict__ out, long long out_stride, long long n_rows,
+                   long long row_bytes, int pieces_per_row) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bars[kGatherWarps][kSlots];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane != 0) return;  // one elected lane per warp drives the copies
+    unsigned char* ring = smem + static_cast<size_t>(warp) * kSlots * kSlotBytes;
+    for (int s = 0; s < kSlots; ++s) mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+    const long long n_items = n_rows * pieces_per_row;
+    const long long gw = static_cast<long long>(blockIdx.x) * kGatherWarps + warp;
+    const long long gstride = static_cast<long long>(gridDim.x) * kGatherWarps;
+    if (gw >= n_items) return;
+    const long long my_count = (n_items - gw + gstride - 1) / gstride;
+
+    auto issue_load = [&](long long n) {
+        const long long item = gw + n * gstride;
+        const long long row = item / pieces_per_row;
+        const int piece = static_cast<int>(item - row * pieces_per_row);
+        const long long off = static_cast<long long>(piece) * kSlotBytes;
+        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(kSlotBytes), row_bytes - off));
+        bool is_host;
+        const char* g = resolve_row(src, row, &is_host) + off;
+        const int slot = static_cast<int>(n % kSlots);
+        mbar_expect_tx(&bars[warp][slot], bytes);
+        bulk_g2s(ring + slot * kSlotBytes, g, bytes, &bars[warp][slot]);
+    };
+    auto issue_store = [&](long long n) {
+        const long long item = gw + n * gstride;
+        const long long row = item / pieces_per_row;
+        const int piece = static_cast<int>(item - row * pieces_per_row);
+        const long long off = static_cast<long long>(piece) * kSlotBytes;
+        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(kSlotBytes), row_bytes - off));
+        const int slot = static_cast<int>(n % kSlots);
+        bulk_s2g(out + row * out_stride + off, ring + slot * kSlotBytes, bytes);
+    };
+
+    const long long pre = min(static_cast<long long>(kSlots), my_count);
+    for (long long n = 0; n < pre; ++n) issue_load(n);
+    for (long long n = 0; n < my_count; ++n) {
+        const int slot = static_cast<int>(n % kSlots);
+        mbar_wait(&bars[warp][slot], static_cast<uint32_t>((n / kSlots) & 1));
+        issue_store(n);
+        // refill the slot of the PREVIOUS store once that store has drained its smem
+        if (n >= 1 && (n - 1) + kSlots < my_count) {
+            bulk_wait_read<1>();
+            issue_load((n - 1) + kSlots);
+        }
+    }
+    bulk_wait_all();
+}
+
+// generic fallback: one warp per row, 16-byte / 4-byte / 1-byte moves by alignment
+__global__ void __launch_bounds__(256)
+gather_ldg_kernel(const GatherSrc src, char* __restrict__ out, long long out_stride, long long n_rows,
+                  long long row_bytes, long long* miss_count) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    bool is_host;
+    const char* s = resolve_row(src, row, &is_host);
+    char* d = out + row * out_stride;
+    if (miss_count && is_host && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(miss_count), 1ull);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) |
+                         static_cast<uintptr_t>(row_bytes);
+    if ((al & 15) == 0) {
+        const long long n16 = row_bytes >> 4;
+        for (long long i = lane; i < n16; i += 32)
+            reinterpret_cast<uint4*>(d)[i] = ldg_nc_u4(reinterpret_cast<const uint4*>(s) + i);
+    } else if ((al & 3) == 0) {
+        const long long n4 = row_bytes >> 2;
+        for (long long i = lane; i < n4; i += 32)
+            reinterpret_cast<uint32_t*>(d)[i] = __ldg(reinterpret_cast<const uint32_t*>(s) + i);
+    } else {
+        for (long long i = lane; i < row_bytes; i += 32) d[i] = s[i];
+    }
+}
+
+}  // namespace dgllb
+
+using namespace dgllb;
+
+static int launch_gather(const GatherSrc& src, void* out, int64_t out_stride, int64_t n_rows,
+                         int64_t row_bytes, bool allow_bulk, long long* miss_count, cudaStream_t st) {
+    const bool bulk_ok = allow_bulk && aligned16(src.table) && aligned16(out) && (src.stride % 16 == 0) &&
+                         (out_stride % 16 == 0) && (row_bytes % 16 == 0) && row_bytes >= 16;
+    if (bulk_ok) {
+        DevInfo di;
+        int rc = get_devinfo(&di);
+        if (rc != DGLLB_OK) return rc;
+        const int pieces = static_cast<int>((row_bytes + kSlotBytes - 1) / kSlotBytes);
+        const size_t smem = static_cast<size_t>(kGatherWarps) * kSlots * kSlotBytes;
+        // opt in to >48 KB dynamic shared memory (idempotent)
+        DGLLB_CUDA_TRY(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+        const long long items = n_rows * pieces;
+        long long blocks = (items + kGatherWarps - 1) / kGatherWarps;
+        const long long max_blocks = static_cast<long long>(di.sm_count);  // 128 KB smem => 1 CTA/SM
+        if (blocks > max_blocks) blocks = max_blocks;
+        gather_bulk_kernel<<<static_cast<unsigned>(blocks), kGatherWarps * 32, smem, st>>>(
+            src, static_cast<char*>(out), out_stride, n_rows, row_bytes, pieces);
+        DGLLB_LAUNCH_CHECK();
+        return DGLLB_OK;
+    }
+    const long long blocks = (n_rows * 32 + 255) / 256;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "gather: grid too large");
+    gather_ldg_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, static_cast<char*>(out), out_stride,
+                                                                     n_rows, row_bytes, miss_count);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+extern "C" int dgllb_gather_rows(const void* table, int64_t table_stride_bytes, const void* ids,
+                                 int ids_is64, void* out, int64_t out_stride_bytes, int64_t n_rows,
+                                 int64_t row_bytes, void* stream) {
+    if (n_rows == 0 || row_bytes == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(table && ids && out, "gather_rows: null pointer");
+    DGLLB_REQUIRE(n_rows > 0 && row_bytes > 0, "gather_rows: negative size");
+    DGLLB_REQUIRE(table_stride_bytes >= row_bytes && out_stride_bytes >= row_bytes,
+                  "gather_rows: stride smaller than row_bytes");
+    GatherSrc s;
+    s.table = static_cast<const char*>(table);
+    s.stride = table_stride_bytes;
+    s.ids = ids;
+    s.ids64 = ids_is64;
+    s.gpu_flag = nullptr;
+    s.local2cache = nullptr;
+    s.nid_map = nullptr;
+    s.host_table = nullptr;
+    s.host_stride = 0;
+    return launch_gather(s, out, out_stride_bytes, n_rows, row_bytes, true, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dgllb_gather_rows_cached(const void* cache_table, int64_t cache_stride_bytes,
+                                        const void* host_table, int64_t host_stride_bytes,
+                                        const int64_t* ids, const uint8_t* gpu_flag,
+                                        const int64_t* localid2cacheid, const int64_t* nid_map,
+                                        void* out, int64_t out_stride_bytes, int64_t n_rows,
+                                        int64_t row_bytes, int64_t* miss_count, void* stream) {
+    if (n_rows == 0 || row_bytes == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(ids && gpu_flag && localid2cacheid && out, "gather_rows_cached: null pointer");
+    DGLLB_REQUIRE(cache_table || host_table, "gather_rows_cached: no table");
+    GatherSrc s;
+    s.table = static_cast<const char*>(cache_table);
+    s.stride = cache_stride_bytes;
+    s.ids = ids;
+    s.ids64 = 1;
+    s.gpu_flag = gpu_flag;
+    s.local2cache = reinterpret_cast<const long long*>(localid2cacheid);
+    s.nid_map = reinterpret_cast<const long long*>(nid_map);
+    s.host_table = static_cast<const char*>(host_table);
+    s.host_stride = host_stride_bytes;
+    // misses read pinned host memory through the PCIe aperture: plain LDGs, not TMA
+    return launch_gather(s, out, out_stride_bytes, n_rows, row_bytes, false,
+                         reinterpret_cast<long long*>(miss_count), static_cast<cudaStream_t>(stream));
+}

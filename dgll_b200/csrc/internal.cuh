@@ -1,0 +1,47 @@
+// internal.cuh — declarations shared between the translation units of the library
+// (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace dgllb {
+
+struct SpmmParams {
+    const void* row_ptr;
+    int rp64;
+    const int* col;
+    const float* vals;
+    const void* X;
+    long long ldx;
+    float* out;
+    long long ldo;
+    long long n_dst;
+    int F;
+    int n_slabs;
+    int mean;
+    const float* row_scale;
+    const float* addend;
+    long long ld_add;
+    const float* bias;
+    int epi;
+    int* argmax;
+    // nnz-split (heavy rows)
+    const int2* heavy_items;  // (row, chunk)
+    long long n_heavy_items;
+    int chunk_edges;          // 0 = no plan
+    const int* row_cnt;       // optional per-row edge-count clamp (legacy num_neighbors)
+};
+
+// run the aggregation kernel(s) for a filled parameter block (spmm.cu)
+int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan, cudaStream_t st);
+
+// exact-fp32 SIMT GEMM (gemm_simt.cu)
+int gemm_simt(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+              long long ldc, long long M, long long N, long long K, const float* bias, int epi,
+              int accumulate, cudaStream_t st);
+
+// tcgen05 bf16 GEMM (gemm_tcgen05.cu); returns DGLLB_ERR_UNSUPPORTED for shapes it does not take
+int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+                 float* C, long long ldc, long long M, long long N, long long K, const float* bias, int epi,
+                 int accumulate, cudaStream_t st);
+
+}  // namespace dgllb

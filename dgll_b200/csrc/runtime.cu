@@ -1,0 +1,70 @@
+// runtime.cu — error string, device-info cache, launch counter.
+#include "common.cuh"
+#include <mutex>
+#include <string.h>
+
+namespace dgllb {
+
+static thread_local char t_err[512] = "";
+std::atomic<long long> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+static const int kMaxDev = 64;
+static DevInfo g_info[kMaxDev];
+static std::atomic<int> g_info_ok[kMaxDev];
+static std::mutex g_info_mu;
+
+int get_devinfo(DevInfo* out) {
+    int dev = 0;
+    DGLLB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) {
+        set_error("device index %d out of range", dev);
+        return DGLLB_ERR_INVALID;
+    }
+    if (!g_info_ok[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(g_info_mu);
+        if (!g_info_ok[dev].load(std::memory_order_relaxed)) {
+            DevInfo d;
+            int v = 0;
+            DGLLB_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+            DGLLB_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+            DGLLB_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+            DGLLB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev));
+            d.l2_bytes = v;
+            DGLLB_CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            g_info[dev] = d;
+            g_info_ok[dev].store(1, std::memory_order_release);
+        }
+    }
+    *out = g_info[dev];
+    return DGLLB_OK;
+}
+
+}  // namespace dgllb
+
+extern "C" {
+
+int dgllb_version(void) { return 1000; }
+
+const char* dgllb_last_error(void) { return dgllb::t_err; }
+
+int dgllb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes) {
+    dgllb::DevInfo d;
+    int rc = dgllb::get_devinfo(&d);
+    if (rc != DGLLB_OK) return rc;
+    if (sm_count) *sm_count = d.sm_count;
+    if (cc_major) *cc_major = d.cc_major;
+    if (cc_minor) *cc_minor = d.cc_minor;
+    if (l2_bytes) *l2_bytes = d.l2_bytes;
+    return DGLLB_OK;
+}
+
+int64_t dgllb_launch_count(void) { return dgllb::g_launch_count.load(); }
+
+}  // extern "C"

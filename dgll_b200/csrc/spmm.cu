@@ -1,0 +1,571 @@
+// spmm.cu — CSR neighbourhood aggregation (SpMM) for sm_100a.
+//
+// Replaces: torch.spmm (dgll/nn/Convolution/gcnconv.py:31), torch.sparse.mm
+// (Evaluation/PPI/gcn_model.py:76), the edge loop of gcn_fused_kernel.cu:41-57,
+// NeighborAggregator mean/sum/max (sageconv.py:32-38), scatter() pooling
+// (GlobalPooling/Pooling.py:37,59,81) and the DGL update_all SpMM behind
+// GraphConv/SAGEConv (GPU Accelerator/CommGNNModel.py:23-28,72-77).
+//
+// Design (HBM-bound gather, no tensor cores):
+//   work item  = (destination row, feature slab); a slab is LANES x 16 bytes of
+//                one feature row, so one LDG.128 per lane fetches a contiguous
+//                512-byte (LANES=32) piece of a source row — fully coalesced;
+//   row-split  : a group of LANES lanes owns an item and walks the row's edges;
+//                column indices are loaded LANES at a time (coalesced) and
+//                broadcast with shuffles; U=8 source rows are in flight per lane;
+//   nnz-split  : with a plan, rows longer than `chunk` edges are cut into
+//                chunks that run first (longest work first) and combine through
+//                128-bit RED.ADD into pre-zeroed rows, then a finalize kernel
+//                applies the epilogue;
+//   reductions : fp32 accumulation in CSR edge order (sum/mean), max with argmax.
+// Algorithmic bytes per launch: nnz*(4 + [4 values] + F*b) + n_dst*(F*4 + r).
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace dgllb {
+
+
+__device__ __forceinline__ long long load_rp(const void* p, int is64, long long i) {
+    return is64 ? reinterpret_cast<const long long*>(p)[i]
+                : static_cast<long long>(reinterpret_cast<const int*>(p)[i]);
+}
+
+__device__ __forceinline__ float apply_epi(float v, int epi) {
+    if (epi & DGLLB_EPI_RELU) v = fmaxf(v, 0.f);
+    if (epi & DGLLB_EPI_ELU) v = v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+// ---------------------------------------------------------------- traits --
+// XT = float : VEC elements per lane = 4 (16 B) or 1
+// XT = __nv_bfloat16 : VEC elements per lane = 8 (16 B) or 1
+template <typename XT, int VE>
+struct RowLoad;
+
+template <>
+struct RowLoad<float, 4> {
+    static constexpr int kAcc = 4;
+    typedef float4 raw_t;
+    __device__ static __forceinline__ raw_t load(const float* p) { return ldg_nc_f4(p); }
+    __device__ static __forceinline__ raw_t zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ static __forceinline__ void unpack(const raw_t& r, float* v) {
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    }
+};
+template <>
+struct RowLoad<float, 1> {
+    static constexpr int kAcc = 1;
+    typedef float raw_t;
+    __device__ static __forceinline__ raw_t load(const float* p) { return ldg_nc_f1(p); }
+    __device__ static __forceinline__ raw_t zero() { return 0.f; }
+    __device__ static __forceinline__ void unpack(const raw_t& r, float* v) { v[0] = r; }
+};
+template <>
+struct RowLoad<__nv_bfloat16, 8> {
+    static constexpr int kAcc = 8;
+    typedef uint4 raw_t;
+    __device__ static __forceinline__ raw_t load(const __nv_bfloat16* p) { return ldg_nc_u4(p); }
+    __device__ static __forceinline__ raw_t zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    __device__ static __forceinline__ void unpack(const raw_t& r, float* v) {
+        v[0] = bf16lo_to_f32(r.x); v[1] = bf16hi_to_f32(r.x);
+        v[2] = bf16lo_to_f32(r.y); v[3] = bf16hi_to_f32(r.y);
+        v[4] = bf16lo_to_f32(r.z); v[5] = bf16hi_to_f32(r.z);
+        v[6] = bf16lo_to_f32(r.w); v[7] = bf16hi_to_f32(r.w);
+    }
+};
+template <>
+struct RowLoad<__nv_bfloat16, 1> {
+    static constexpr int kAcc = 1;
+    typedef unsigned short raw_t;
+    __device__ static __forceinline__ raw_t load(const __nv_bfloat16* p) {
+        return __ldg(reinterpret_cast<const unsigned short*>(p));
+    }
+    __device__ static __forceinline__ raw_t zero() { return 0; }
+    __device__ static __forceinline__ void unpack(const raw_t& r, float* v) {
+        v[0] = __uint_as_float(static_cast<uint32_t>(r) << 16);
+    }
+};
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 8;
+
+// ------------------------------------------------------------ main kernel --
+template <typename XT, int VE, int LANES, bool IS_MAX>
+__global__ void __launch_bounds__(kThreads)
+spmm_rowslab_kernel(const SpmmParams p) {
+    typedef RowLoad<XT, VE> L;
+    constexpr int A = L::kAcc;
+    const int lig = threadIdx.x & (LANES - 1);                 // lane in group
+    const long long group = (static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x) / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu
+                                         : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
+
+    const long long n_heavy_groups = p.n_heavy_items * p.n_slabs;
+    long long row, beg, end, deg;
+    int slab;
+    bool heavy = false;
+    if (group < n_heavy_groups) {
+        const long long it = group / p.n_slabs;
+        slab = static_cast<int>(group - it * p.n_slabs);
+        const int2 hc = p.heavy_items[it];
+        row = hc.x;
+        const long long rb = load_rp(p.row_ptr, p.rp64, row);
+        const long long re = load_rp(p.row_ptr, p.rp64, row + 1);
+        deg = re - rb;
+        beg = rb + static_cast<long long>(hc.y) * p.chunk_edges;
+        end = min(re, beg + p.chunk_edges);
+        heavy = true;
+    } else {
+        const long long g2 = group - n_heavy_groups;
+        row = g2 / p.n_slabs;
+        if (row >= p.n_dst) return;
+        slab = static_cast<int>(g2 - row * p.n_slabs);
+        beg = load_rp(p.row_ptr, p.rp64, row);
+        end = load_rp(p.row_ptr, p.rp64, row + 1);
+        if (p.row_cnt) end = min(end, beg + max(0, __ldg(p.row_cnt + row)));  // legacy num_neighbors guard
+        deg = end - beg;
+        if (!IS_MAX && p.chunk_edges > 0 && deg > p.chunk_edges) return;  // done by heavy items
+    }
+
+    const int col0 = (slab * LANES + lig) * A;  // first feature column of this lane
+    const bool lane_on = col0 < p.F;
+    const XT* __restrict__ Xb = reinterpret_cast<const XT*>(p.X) + col0;
+
+    float acc[A];
+    int amax[IS_MAX ? A : 1];
+#pragma unroll
+    for (int a = 0; a < A; ++a) acc[a] = IS_MAX ? -INFINITY : 0.f;
+    if (IS_MAX) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) amax[a] = -1;
+    }
+
+    for (long long e0 = beg; e0 < end; e0 += LANES) {
+        const int n = static_cast<int>(min(static_cast<long long>(LANES), end - e0));
+        long long my_c = 0;
+        float my_w = 1.f;
+        if (lig < n) {
+            my_c = p.col ? static_cast<long long>(__ldg(p.col + e0 + lig)) : (e0 + lig);
+            if (p.vals) my_w = __ldg(p.vals + e0 + lig);
+        }
+        for (int k = 0; k < n; k += kUnroll) {
+            typename L::raw_t raw[kUnroll];
+            float w[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int src = (k + u) & (LANES - 1);
+                // identity-column mode can exceed int32; shuffle the 64-bit index as two halves
+                long long c;
+                if (p.col) {
+                    c = static_cast<long long>(__shfl_sync(gmask, static_cast<int>(my_c), src, LANES));
+                } else {
+                    c = __shfl_sync(gmask, my_c, src, LANES);
+                }
+                w[u] = __shfl_sync(gmask, my_w, src, LANES);
+                if (k + u < n && lane_on) {
+                    raw[u] = L::load(Xb + c * p.ldx);
+                } else {
+                    raw[u] = L::zero();
+                    w[u] = IS_MAX ? NAN : 0.f;  // NAN marks "no edge" for max
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                float v[A];
+                L::unpack(raw[u], v);
+                if (IS_MAX) {
+                    if (w[u] == w[u]) {  // not the NAN marker
+#pragma unroll
+                        for (int a = 0; a < A; ++a) {
+                            const float t = w[u] * v[a];
+                            if (t > acc[a]) {
+                                acc[a] = t;
+                                amax[a] = static_cast<int>(e0 + k + u);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < A; ++a) acc[a] = fmaf(w[u], v[a], acc[a]);
+                }
+            }
+        }
+    }
+
+    if (!lane_on) return;
+
+    float scale = 1.f;
+    if (p.mean) scale = deg > 0 ? 1.f / static_cast<float>(deg) : 0.f;
+    if (p.row_scale) scale *= __ldg(p.row_scale + row);
+    if (IS_MAX && deg == 0) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) acc[a] = 0.f;
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) acc[a] *= scale;
+
+    float* __restrict__ o = p.out + row * p.ldo + col0;
+    const int valid = min(A, p.F - col0);
+
+    if (heavy) {
+        // partial sums of a split row: combine with RED.ADD (rows were pre-zeroed);
+        // epilogue runs in spmm_finalize_heavy_kernel.
+        if (A == 4 && valid == 4) {
+            atomicAdd(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        } else {
+#pragma unroll
+            for (int a = 0; a < A; ++a)
+                if (a < valid) atomicAdd(o + a, acc[a]);
+        }
+        return;
+    }
+
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        if (a < valid) {
+            float v = acc[a];
+            if (p.addend) v += __ldg(p.addend + row * p.ld_add + col0 + a);
+            if (p.bias) v += __ldg(p.bias + col0 + a);
+            acc[a] = apply_epi(v, p.epi);
+        }
+    }
+    if (A >= 4 && valid == A) {
+#pragma unroll
+        for (int a = 0; a < A; a += 4)
+            stg_cs_f4(o + a, make_float4(acc[a], acc[a + 1], acc[a + 2], acc[a + 3]));
+    } else {
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+            if (a < valid) o[a] = acc[a];
+    }
+    if (IS_MAX && p.argmax) {
+        int* am = p.argmax + row * static_cast<long long>(p.F) + col0;
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+            if (a < valid) am[a] = amax[a];
+    }
+}
+
+// zero the output rows of split rows before the RED.ADDs land
+__global__ void spmm_zero_heavy_kernel(const int* heavy_rows, long long n_heavy, float* out,
+                                       long long ldo, int F) {
+    const long long r = blockIdx.x;
+    if (r >= n_heavy) return;
+    float* o = out + static_cast<long long>(heavy_rows[r]) * ldo;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) o[f] = 0.f;
+}
+
+__global__ void spmm_finalize_heavy_kernel(const int* heavy_rows, long long n_heavy, float* out,
+                                           long long ldo, int F, const float* addend,
+                                           long long ld_add, const float* bias, int epi) {
+    const long long r = blockIdx.x;
+    if (r >= n_heavy) return;
+    const long long row = heavy_rows[r];
+    float* o = out + row * ldo;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float v = o[f];
+        if (addend) v += addend[row * ld_add + f];
+        if (bias) v += bias[f];
+        o[f] = apply_epi(v, epi);
+    }
+}
+
+// ------------------------------------------------------------------ plan --
+__global__ void plan_count_kernel(const void* row_ptr, int rp64, long long n_rows, int chunk,
+                                  unsigned long long* counters) {
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const long long deg = load_rp(row_ptr, rp64, r + 1) - load_rp(row_ptr, rp64, r);
+    if (deg > chunk) {
+        atomicAdd(&counters[0], 1ull);
+        atomicAdd(&counters[1], static_cast<unsigned long long>((deg + chunk - 1) / chunk));
+    }
+}
+
+__global__ void plan_fill_kernel(const void* row_ptr, int rp64, long long n_rows, int chunk,
+                                 unsigned long long* counters, int* heavy_rows, int2* items) {
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const long long deg = load_rp(row_ptr, rp64, r + 1) - load_rp(row_ptr, rp64, r);
+    if (deg > chunk) {
+        const unsigned long long hi = atomicAdd(&counters[2], 1ull);
+        heavy_rows[hi] = static_cast<int>(r);
+        const int nc = static_cast<int>((deg + chunk - 1) / chunk);
+        const unsigned long long base = atomicAdd(&counters[3], static_cast<unsigned long long>(nc));
+        for (int k = 0; k < nc; ++k) items[base + k] = make_int2(static_cast<int>(r), k);
+    }
+}
+
+}  // namespace dgllb
+
+struct dgllb_csr_plan {
+    int chunk_edges;
+    long long n_rows;
+    long long n_heavy_rows;
+    long long n_items;
+    int* heavy_rows;  // device
+    int2* items;      // device
+};
+
+using namespace dgllb;
+
+extern "C" int dgllb_csr_plan_create(const void* row_ptr, int row_ptr_is64, int64_t n_rows,
+                                     int chunk_edges, void* stream, dgllb_csr_plan** plan_out) {
+    DGLLB_REQUIRE(row_ptr && plan_out, "csr_plan_create: null pointer");
+    DGLLB_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "csr_plan_create: n_rows out of range");
+    if (chunk_edges <= 0) chunk_edges = 4096;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long* d_cnt = nullptr;
+    DGLLB_CUDA_TRY(cudaMalloc(&d_cnt, 4 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), st);
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
+    const int tb = 256;
+    const unsigned grid = static_cast<unsigned>((n_rows + tb - 1) / tb);
+    if (e == cudaSuccess && n_rows > 0) {
+        plan_count_kernel<<<grid, tb, 0, st>>>(row_ptr, row_ptr_is64, n_rows, chunk_edges, d_cnt);
+        g_launch_count.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(d_cnt);
+        set_error("csr_plan_create: %s", cudaGetErrorString(e));
+        return DGLLB_ERR_CUDA;
+    }
+    dgllb_csr_plan* pl = new dgllb_csr_plan();
+    pl->chunk_edges = chunk_edges;
+    pl->n_rows = n_rows;
+    pl->n_heavy_rows = static_cast<long long>(h_cnt[0]);
+    pl->n_items = static_cast<long long>(h_cnt[1]);
+    pl->heavy_rows = nullptr;
+    pl->items = nullptr;
+    if (pl->n_heavy_rows > 0) {
+        e = cudaMalloc(&pl->heavy_rows, pl->n_heavy_rows * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&pl->items, pl->n_items * sizeof(int2));
+        if (e == cudaSuccess) {
+            plan_fill_kernel<<<grid, tb, 0, st>>>(row_ptr, row_ptr_is64, n_rows, chunk_edges, d_cnt,
+                                                  pl->heavy_rows, pl->items);
+            g_launch_count.fetch_add(1);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(d_cnt);
+            dgllb_csr_plan_destroy(pl);
+            set_error("csr_plan_create: %s", cudaGetErrorString(e));
+            return DGLLB_ERR_CUDA;
+        }
+    }
+    cudaFree(d_cnt);
+    *plan_out = pl;
+    return DGLLB_OK;
+}
+
+extern "C" int dgllb_csr_plan_info(const dgllb_csr_plan* plan, int64_t* n_heavy_rows,
+                                   int64_t* n_chunks, int* chunk_edges) {
+    DGLLB_REQUIRE(plan, "csr_plan_info: null plan");
+    if (n_heavy_rows) *n_heavy_rows = plan->n_heavy_rows;
+    if (n_chunks) *n_chunks = plan->n_items;
+    if (chunk_edges) *chunk_edges = plan->chunk_edges;
+    return DGLLB_OK;
+}
+
+extern "C" void dgllb_csr_plan_destroy(dgllb_csr_plan* plan) {
+    if (!plan) return;
+    if (plan->heavy_rows) cudaFree(plan->heavy_rows);
+    if (plan->items) cudaFree(plan->items);
+    delete plan;
+}
+
+// --------------------------------------------------------------- dispatch --
+template <typename XT, int VE, int LANES>
+static int launch_spmm(const SpmmParams& p, bool is_max, cudaStream_t st) {
+    const long long groups = (p.n_heavy_items + p.n_dst) * p.n_slabs;
+    if (groups == 0) return DGLLB_OK;
+    const int gpb = kThreads / LANES;
+    const long long blocks = (groups + gpb - 1) / gpb;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "spmm: grid too large (%lld blocks)", blocks);
+    if (is_max)
+        spmm_rowslab_kernel<XT, VE, LANES, true><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
+    else
+        spmm_rowslab_kernel<XT, VE, LANES, false><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+template <typename XT, int VE>
+static int launch_spmm_lanes(SpmmParams& p, bool is_max, cudaStream_t st) {
+    // smallest group whose slab covers F, so narrow rows do not idle lanes
+    const int per_lane = VE;
+    if (VE > 1 && p.F <= 8 * per_lane) {
+        p.n_slabs = 1;
+        return launch_spmm<XT, VE, 8>(p, is_max, st);
+    }
+    if (VE > 1 && p.F <= 16 * per_lane) {
+        p.n_slabs = 1;
+        return launch_spmm<XT, VE, 16>(p, is_max, st);
+    }
+    p.n_slabs = (p.F + 32 * per_lane - 1) / (32 * per_lane);
+    return launch_spmm<XT, VE, 32>(p, is_max, st);
+}
+
+namespace dgllb {
+int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan, cudaStream_t st) {
+    const bool use_plan = plan && !is_max && plan->n_heavy_rows > 0 && !p.row_cnt;
+    if (use_plan) {
+        p.heavy_items = plan->items;
+        p.n_heavy_items = plan->n_items;
+        p.chunk_edges = plan->chunk_edges;
+        spmm_zero_heavy_kernel<<<static_cast<unsigned>(plan->n_heavy_rows), 128, 0, st>>>(
+            plan->heavy_rows, plan->n_heavy_rows, p.out, p.ldo, p.F);
+        DGLLB_LAUNCH_CHECK();
+    }
+    int rc;
+    if (x_dtype == DGLLB_F32) {
+        const bool vec = aligned16(p.X) && aligned16(p.out) && (p.ldx % 4 == 0) && (p.ldo % 4 == 0);
+        rc = vec ? launch_spmm_lanes<float, 4>(p, is_max, st) : launch_spmm_lanes<float, 1>(p, is_max, st);
+    } else {
+        const bool vec = aligned16(p.X) && aligned16(p.out) && (p.ldx % 8 == 0) && (p.ldo % 4 == 0);
+        rc = vec ? launch_spmm_lanes<__nv_bfloat16, 8>(p, is_max, st)
+                 : launch_spmm_lanes<__nv_bfloat16, 1>(p, is_max, st);
+    }
+    if (rc != DGLLB_OK) return rc;
+    if (use_plan && (p.addend || p.bias || p.epi)) {
+        spmm_finalize_heavy_kernel<<<static_cast<unsigned>(plan->n_heavy_rows), 128, 0, st>>>(
+            plan->heavy_rows, plan->n_heavy_rows, p.out, p.ldo, p.F, p.addend, p.ld_add, p.bias, p.epi);
+        DGLLB_LAUNCH_CHECK();
+    }
+    return DGLLB_OK;
+}
+}  // namespace dgllb
+
+extern "C" int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                              const float* values, const void* X, int x_dtype, int64_t ldx,
+                              float* out, int64_t ldo, int64_t n_dst, int64_t n_src, int F,
+                              int reduce, const float* row_scale, const float* addend,
+                              int64_t ld_add, const float* bias, int epilogue,
+                              int32_t* argmax_out, const dgllb_csr_plan* plan, void* stream) {
+    DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && F >= 0, "spmm: negative size");
+    if (n_dst == 0 || F == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(row_ptr && X && out, "spmm: null pointer");
+    DGLLB_REQUIRE(ldx >= F && ldo >= F, "spmm: leading dimension smaller than F (ldx=%lld ldo=%lld F=%d)",
+                  (long long)ldx, (long long)ldo, F);
+    DGLLB_REQUIRE(reduce == DGLLB_SUM || reduce == DGLLB_MEAN || reduce == DGLLB_MAX,
+                  "spmm: unknown reduce %d", reduce);
+    DGLLB_REQUIRE(x_dtype == DGLLB_F32 || x_dtype == DGLLB_BF16, "spmm: unknown dtype %d", x_dtype);
+    DGLLB_REQUIRE(!addend || ld_add >= F, "spmm: ld_add smaller than F");
+    DGLLB_REQUIRE(n_dst < (1ll << 31), "spmm: n_dst must fit int32");
+    DGLLB_REQUIRE(!plan || plan->n_rows == n_dst, "spmm: plan was built for %lld rows, got %lld",
+                  plan ? plan->n_rows : 0ll, (long long)n_dst);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SpmmParams p;
+    p.row_ptr = row_ptr;
+    p.rp64 = row_ptr_is64;
+    p.col = col_idx;
+    p.vals = values;
+    p.X = X;
+    p.ldx = ldx;
+    p.out = out;
+    p.ldo = ldo;
+    p.n_dst = n_dst;
+    p.F = F;
+    p.n_slabs = 1;
+    p.mean = reduce == DGLLB_MEAN;
+    p.row_scale = row_scale;
+    p.addend = addend;
+    p.ld_add = ld_add;
+    p.bias = bias;
+    p.epi = epilogue;
+    p.argmax = argmax_out;
+    p.heavy_items = nullptr;
+    p.n_heavy_items = 0;
+    p.chunk_edges = 0;
+    p.row_cnt = nullptr;
+    return spmm_run(p, x_dtype, reduce == DGLLB_MAX, plan, st);
+}
+
+// ----------------------------------------------------------------- SDDMM --
+namespace dgllb {
+
+// one warp per row; the row of A stays in registers (F <= 32*4*kMaxChunks) and
+// each edge's row of B streams through with 128-bit loads.
+template <int VE>
+__global__ void __launch_bounds__(256)
+sddmm_kernel(const void* row_ptr, int rp64, const int* __restrict__ col, const float* __restrict__ A,
+             long long lda, const float* __restrict__ B, long long ldb, float* __restrict__ out_e,
+             long long n_rows, int F) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const long long beg = load_rp(row_ptr, rp64, row), end = load_rp(row_ptr, rp64, row + 1);
+    const float* a = A + row * lda;
+    for (long long e = beg; e < end; ++e) {
+        const float* b = B + static_cast<long long>(__ldg(col + e)) * ldb;
+        float s = 0.f;
+        if (VE == 4) {
+            for (int f = lane * 4; f < F; f += 128) {
+                if (f + 4 <= F) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(a + f));
+                    const float4 y = ldg_nc_f4(b + f);
+                    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s);
+                    s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+                } else {
+                    for (int t = f; t < F; ++t) s = fmaf(__ldg(a + t), __ldg(b + t), s);
+                }
+            }
+        } else {
+            for (int f = lane; f < F; f += 32) s = fmaf(__ldg(a + f), __ldg(b + f), s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) out_e[e] = s;
+    }
+}
+
+__global__ void max_backward_kernel(const int* __restrict__ col, const int* __restrict__ argmax,
+                                    const float* __restrict__ g, long long ldg, float* gx,
+                                    long long ldx, long long n_dst, int F) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_dst * F) return;
+    const long long r = i / F;
+    const int f = static_cast<int>(i - r * F);
+    const int e = argmax[i];
+    if (e >= 0) atomicAdd(gx + static_cast<long long>(col ? col[e] : e) * ldx + f, g[r * ldg + f]);
+}
+
+}  // namespace dgllb
+
+extern "C" int dgllb_sddmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                               const float* A, int64_t lda, const float* B, int64_t ldb,
+                               float* out_e, int64_t n_rows, int F, void* stream) {
+    if (n_rows == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(row_ptr && col_idx && A && B && out_e, "sddmm: null pointer");
+    DGLLB_REQUIRE(lda >= F && ldb >= F && F >= 0, "sddmm: bad leading dimension");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long blocks = (n_rows * 32 + 255) / 256;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "sddmm: grid too large");
+    const bool vec = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0;
+    if (vec)
+        sddmm_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(row_ptr, row_ptr_is64, col_idx, A, lda,
+                                                                       B, ldb, out_e, n_rows, F);
+    else
+        sddmm_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(row_ptr, row_ptr_is64, col_idx, A, lda,
+                                                                       B, ldb, out_e, n_rows, F);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+extern "C" int dgllb_spmm_max_backward(const int32_t* col_idx, const int32_t* argmax,
+                                       const float* grad_out, int64_t ldg, float* grad_X,
+                                       int64_t ldx, int64_t n_dst, int F, void* stream) {
+    if (n_dst == 0 || F == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(argmax && grad_out && grad_X, "max_backward: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = n_dst * F;
+    const long long blocks = (total + 255) / 256;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "max_backward: grid too large");
+    max_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(col_idx, argmax, grad_out, ldg, grad_X,
+                                                                       ldx, n_dst, F);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}

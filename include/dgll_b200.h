@@ -1,0 +1,323 @@
+/*
+ * dgll_b200.h — C ABI of the B200-native neighbourhood-aggregation path.
+ *
+ * This is the drop-in boundary for the hot path of dke-lab/dgll: every entry
+ * point takes plain device pointers + sizes + a CUDA stream (as void*), never
+ * a torch type, and returns an int status (0 = OK) instead of calling
+ * exit(1).  Each declaration cites the reference interface it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions (all entry points unless stated otherwise)
+ *   - pointers are DEVICE pointers borrowed from the caller (caller owns/frees);
+ *   - `stream` is a cudaStream_t cast to void* (NULL = legacy default stream);
+ *     calls are stream-ordered and do NOT synchronise the device;
+ *   - thread-safe: no global mutable state besides per-device cached properties
+ *     and a thread-local error string (dgllb_last_error);
+ *   - leading dimensions (ld*) are in ELEMENTS, sizes are element/row counts;
+ *   - return codes: DGLLB_OK, DGLLB_ERR_INVALID (bad argument),
+ *     DGLLB_ERR_CUDA (a CUDA call failed; message in dgllb_last_error),
+ *     DGLLB_ERR_UNSUPPORTED (shape/dtype not supported by this build).
+ *
+ * The two legacy symbols at the bottom keep the reference's exact C ABI
+ * (dgll/FusedKernel/gcn_fused_kernel.cu:190-195,238-244).
+ */
+#ifndef DGLL_B200_H_
+#define DGLL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGLLB_OK 0
+#define DGLLB_ERR_INVALID 1
+#define DGLLB_ERR_CUDA 2
+#define DGLLB_ERR_UNSUPPORTED 3
+
+/* reduce ops (NeighborAggregator aggr_method, dgll/nn/Convolution/sageconv.py:32-38;
+ * Pooling reduce=, dgll/nn/GlobalPooling/Pooling.py:37,59,81) */
+#define DGLLB_SUM 0
+#define DGLLB_MEAN 1
+#define DGLLB_MAX 2
+
+/* feature dtypes */
+#define DGLLB_F32 0
+#define DGLLB_BF16 1
+
+/* epilogue flags */
+#define DGLLB_EPI_RELU 1 /* fmaxf(x,0) as gcn_fused_kernel.cu:67 */
+#define DGLLB_EPI_ELU 2  /* F.elu as gatconv.py:143-145 */
+
+/* GAT score variants */
+#define DGLLB_GAT_SOFTMAX 0     /* softmax_j(leakyrelu(.)), gatconv.py:30-54 (dense gatConv) */
+#define DGLLB_GAT_EXP_NEG 1     /* exp(-leakyrelu(.))/rowsum, gatconv.py:125-139 (sparseGatConv) */
+
+/* ---------------------------------------------------------------- misc -- */
+
+/* ABI version of this library (major*1000+minor). */
+int dgllb_version(void);
+/* Thread-local, NUL-terminated description of the last error on this thread. */
+const char* dgllb_last_error(void);
+/* Properties of the CURRENT device (cached per device). Any pointer may be NULL. */
+int dgllb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+/* Number of kernels this library has launched on this process (all threads).
+ * bench.py reads it to report `gpu_launches`. */
+int64_t dgllb_launch_count(void);
+
+/* ---------------------------------------------------- CSR aggregation -- */
+
+/*
+ * Opaque load-balancing plan for a static CSR (rows longer than a chunk are
+ * split into nnz-chunks that are reduced with atomics).  Optional: every
+ * aggregation entry point accepts plan == NULL (pure row-split).
+ * Replaces nothing in the reference (it launches one block per row,
+ * gcn_fused_kernel.cu:211); it exists because Reddit-shaped degree skew needs it.
+ * dgllb_csr_plan_create synchronises `stream` once (reads back the item count).
+ */
+typedef struct dgllb_csr_plan dgllb_csr_plan;
+int dgllb_csr_plan_create(const void* row_ptr, int row_ptr_is64, int64_t n_rows,
+                          int chunk_edges /* 0 = default */, void* stream,
+                          dgllb_csr_plan** plan_out);
+int dgllb_csr_plan_info(const dgllb_csr_plan* plan, int64_t* n_heavy_rows,
+                        int64_t* n_chunks, int* chunk_edges);
+void dgllb_csr_plan_destroy(dgllb_csr_plan* plan);
+
+/*
+ * out[i, 0:F] = epi( row_scale[i] * reduce_{e in [row_ptr[i], row_ptr[i+1])}
+ *                     ( values[e] * X[col_idx[e], 0:F] )  + addend[i, 0:F] + bias[0:F] )
+ *
+ * The SpMM behind: torch.spmm(adj, support) dgll/nn/Convolution/gcnconv.py:31;
+ * torch.sparse.mm Evaluation/PPI/gcn_model.py:76; the aggregation loop
+ * gcn_fused_kernel.cu:41-57; NeighborAggregator mean/sum/max sageconv.py:32-38;
+ * DGL GraphConv/SAGEConv update_all as called at GPU Accelerator/CommGNNModel.py:23-28,72-77;
+ * GinConv Adj@Feat ginconv.py:27; scatter() pooling Pooling.py:37,59,81
+ * (pass col_idx == NULL: identity columns, i.e. a segment reduce).
+ *
+ *   row_ptr     int32[n_dst+1] or int64[n_dst+1] (row_ptr_is64)
+ *   col_idx     int32[nnz] (rows of X; NULL = identity: column e is row e)
+ *   values      float[nnz] or NULL (all ones)
+ *   X           x_dtype[n_src, ldx] row-major (DGLLB_F32 / DGLLB_BF16), F <= ldx
+ *   out         float[n_dst, ldo]
+ *   reduce      DGLLB_SUM / DGLLB_MEAN (divide by row degree; empty row -> 0) /
+ *               DGLLB_MAX (empty row -> 0)
+ *   row_scale   float[n_dst] or NULL; addend float[n_dst, ld_add] or NULL;
+ *   bias        float[F] or NULL; epilogue = bit-or of DGLLB_EPI_*
+ *   argmax_out  int32[n_dst, F] or NULL (DGLLB_MAX only): edge index e that won,
+ *               -1 for empty rows (needed by the max backward)
+ * 128-bit vector loads are used when X/out/addend are 16-byte aligned and the
+ * leading dimensions are multiples of 4 (f32) / 8 (bf16); otherwise a scalar
+ * path runs.  accumulation is fp32 in CSR edge order per row (deterministic
+ * unless `plan` splits the row).
+ */
+int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                   const float* values, const void* X, int x_dtype, int64_t ldx,
+                   float* out, int64_t ldo, int64_t n_dst, int64_t n_src, int F,
+                   int reduce, const float* row_scale, const float* addend,
+                   int64_t ld_add, const float* bias, int epilogue,
+                   int32_t* argmax_out, const dgllb_csr_plan* plan, void* stream);
+
+/*
+ * SDDMM: out_e[e] = < A[row(e), 0:F], B[col_idx[e], 0:F] > for every CSR edge.
+ * Replaces the dense N x N product + gather in SpecialSpmmFunction.backward,
+ * dgll/nn/Convolution/gatconv.py:76-78.
+ */
+int dgllb_sddmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                    const float* A, int64_t lda, const float* B, int64_t ldb,
+                    float* out_e, int64_t n_rows, int F, void* stream);
+
+/*
+ * Scatter for the MAX backward: grad_X[col_idx[argmax[i,f]], f] += grad_out[i,f].
+ * grad_X must be pre-zeroed by the caller.
+ */
+int dgllb_spmm_max_backward(const int32_t* col_idx, const int32_t* argmax,
+                            const float* grad_out, int64_t ldg, float* grad_X,
+                            int64_t ldx, int64_t n_dst, int F, void* stream);
+
+/*
+ * CSR transpose (stable sort by column): builds the CSR of A^T, carrying an
+ * optional per-edge value array and producing the edge permutation
+ * perm[e_T] = e (index of the same edge in the input CSR).  Used for
+ * grad_X = A^T grad_out (gatconv.py:80 `a.t().matmul(grad_output)`).
+ * All outputs are caller-allocated: t_row_ptr (same width as row_ptr)[n_cols+1],
+ * t_col_idx int32[nnz], t_values float[nnz] or NULL (ones when values == NULL),
+ * perm int32[nnz] or NULL.  Within a transposed row, edges keep source-row
+ * order (stable), so the result is deterministic.  nnz must be < 2^31-1.
+ * Workspace comes from the stream-ordered allocator (cudaMallocAsync).
+ */
+int dgllb_csr_transpose(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                        const float* values, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                        void* t_row_ptr, int32_t* t_col_idx, float* t_values,
+                        int32_t* perm, void* stream);
+
+/* ------------------------------------------------------ feature gather -- */
+
+/*
+ * out[i, 0:row_bytes) = table[ids[i], 0:row_bytes)   (exact byte copy)
+ * Replaces features[nodes] dgll/data/dgraph.py:105 and the cache gather
+ * gpu_fix_cache[name][cacheid] dgll/FeatureCache/storage.py:185-187,205-209.
+ * ids are int64 (ids_is64) or int32.  Rows move as TMA bulk copies
+ * (global->shared->global) when table/out base and strides are multiples of
+ * 16 bytes; otherwise a vector/scalar LDG path runs.  ids are NOT range-checked.
+ */
+int dgllb_gather_rows(const void* table, int64_t table_stride_bytes, const void* ids,
+                      int ids_is64, void* out, int64_t out_stride_bytes, int64_t n_rows,
+                      int64_t row_bytes, void* stream);
+
+/*
+ * GraphCacheServer.fetch_data split gather (storage.py:151-198):
+ *   hit  (gpu_flag[id] != 0): out[i] = cache_table[localid2cacheid[id]]
+ *   miss                    : out[i] = host_table[nid_map ? nid_map[id] : id]
+ * host_table must be device-accessible (pinned+mapped host memory or device memory).
+ * miss_count (device int64*, may be NULL) is atomically incremented by the number
+ * of misses (storage.py:213-215 try_num/miss_num accounting).
+ */
+int dgllb_gather_rows_cached(const void* cache_table, int64_t cache_stride_bytes,
+                             const void* host_table, int64_t host_stride_bytes,
+                             const int64_t* ids, const uint8_t* gpu_flag,
+                             const int64_t* localid2cacheid, const int64_t* nid_map,
+                             void* out, int64_t out_stride_bytes, int64_t n_rows,
+                             int64_t row_bytes, int64_t* miss_count, void* stream);
+
+/* -------------------------------------------------- dense transform X.W -- */
+
+/*
+ * C[M,N] = epi( A[M,K] . B[K,N] + bias[N] ), all row-major fp32 in HBM.
+ * precision 0: exact fp32 FMA (SIMT) — the parity path (<=1e-5 rel);
+ * precision 1: tcgen05 tensor cores, bf16 operands (converted on the fly),
+ *              fp32 accumulate in TMEM — the fast path (<=1e-2 rel).
+ * transA / transB: use A^T (A stored [K,M]) / B^T (B stored [N,K]).
+ * Replaces torch.mm(x, W) gcnconv.py:30, gcn_model.py:70, gatconv.py:117 and the
+ * per-edge recomputed transform of gcn_fused_kernel.cu:46-54.
+ */
+int dgllb_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb,
+                   int transB, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                   const float* bias, int epilogue, int accumulate, int precision,
+                   void* stream);
+
+/* --------------------------------------------------------- fused GAT ---- */
+
+/*
+ * Fused SDDMM + edge-softmax + aggregation for multi-head GAT.
+ *   z_e   = leakyrelu_slope( el[i,h] + er[j,h] )        i = row (dst), j = col_idx[e]
+ *   mode DGLLB_GAT_SOFTMAX : alpha_e = softmax over row i of (+z_e)
+ *   mode DGLLB_GAT_EXP_NEG : alpha_e = exp(-z_e) / sum_row exp(-z_e)
+ *   out[i,h,:] = epi( sum_e alpha_e * Wh[j,h,:] )
+ * computed in one pass with an online (running-max) softmax; the [E] score
+ * vector is never materialised.  Replaces gatconv.py:117-139 (sparseGatConv,
+ * two COO SpMMs + edge cat) and :30-54 (dense N^2 softmax).
+ *   Wh  float[n_src, ldw]  heads*D <= ldw, head h occupies columns [h*D,(h+1)*D)
+ *   el  float[n_dst, ld_e] (first `heads` columns), er float[n_src, ld_e]
+ *       (el_i = a_l . Wh_i, er_j = a_r . Wh_j; with W extended by the columns
+ *        W_h a_l,h and W_h a_r,h the dense transform emits Wh, el, er in one GEMM)
+ *   out float[n_dst, ldo]
+ *   row_max / row_sum: float[n_dst, heads] (compact) or NULL — saved for the backward
+ *   (max of signed score, sum of exp(score - max)); rows without edges give out = 0.
+ */
+int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                      const float* Wh, int64_t ldw, const float* el, const float* er,
+                      int64_t ld_e, float* out, int64_t ldo, float* row_max, float* row_sum,
+                      int64_t n_dst, int64_t n_src, int heads, int D, float slope,
+                      int mode, int epilogue, void* stream);
+
+/*
+ * Backward of dgllb_gat_forward (epilogue gradient already applied by the caller):
+ * given g = dL/dout [n_dst, ldg] computes
+ *   d_el[n_dst, ld_de], d_er[n_src, ld_de] (first `heads` columns), d_Wh[n_src, ldd]
+ * Pass 1 runs over the forward CSR: recomputes alpha, forms dalpha = <g_i, Wh_j>
+ * (the SDDMM) and writes (alpha, dz) per (edge, head) to `edge_ws`
+ * float[2*nnz*heads] (8-byte aligned); pass 2 runs over the transposed CSR
+ * (t_row_ptr/t_col_idx/perm from dgllb_csr_transpose) and accumulates
+ * d_Wh_j = sum_i alpha_ij g_i and d_er_j.  No atomics: deterministic.
+ * `out` is the forward output BEFORE the epilogue activation.
+ * Replaces SpecialSpmmFunction.backward gatconv.py:71-81 + autograd of :117-139.
+ */
+int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                       const void* t_row_ptr, const int32_t* t_col_idx, const int32_t* perm,
+                       const float* Wh, int64_t ldw, const float* el, const float* er,
+                       int64_t ld_e, const float* out, int64_t ldo, const float* row_max,
+                       const float* row_sum, const float* g, int64_t ldg, float* d_Wh,
+                       int64_t ldd, float* d_el, float* d_er, int64_t ld_de, float* edge_ws,
+                       int64_t n_dst, int64_t n_src, int heads, int D, float slope,
+                       int mode, void* stream);
+
+/* ------------------------------------------------- binarized aggregation -- */
+
+/*
+ * Bit-pack the sign of a feature table: bit f of word (f/32) of row r is
+ * (X[r,f] >= 0).  Pad bits are 0.  words_per_row >= ceil(F/32).
+ * The reference only names this feature (README.md:11); semantics are
+ * defined in SURVEY.md §8 a18.
+ */
+int dgllb_binarize_pack(const float* X, int64_t ldx, uint32_t* packed,
+                        int64_t words_per_row, int64_t n_rows, int F, void* stream);
+
+/*
+ * cnt[i,f] = sum_{e in row i} bit f of packed[col_idx[e]]          (int32, exact)
+ * out modes: 0 = counts as int32; 1 = float sum of +-1 (2*cnt - deg);
+ *            2 = float mean of +-1 ((2*cnt - deg)/deg, empty row -> 0).
+ * Popcount formulation: 32 neighbours' words are bit-transposed across the
+ * warp and __popc'd into per-feature counters.
+ */
+int dgllb_bin_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                       const uint32_t* packed, int64_t words_per_row, void* out,
+                       int64_t ldo, int64_t n_dst, int F, int out_mode, void* stream);
+
+/* ------------------------------------------------ sampling / blocks ------ */
+
+/*
+ * Uniform neighbour sampling WITHOUT replacement, min(deg, fanout) per seed
+ * (the device-side counterpart of Base_sampler.sample_neighbours,
+ * dgll/sampling/base_sampler.py:45-58; fanout < 0 keeps all neighbours).
+ * Output is a CSR block by destination with GLOBAL source ids:
+ *   out_row_ptr int32[n_seeds+1] (exclusive scan of min(deg,fanout)),
+ *   out_col     int32[>= n_seeds*fanout] (caller-sized; exact nnz = out_row_ptr[n_seeds]).
+ * Neighbour order inside a row is the order of the sampled positions
+ * (ascending position), deterministic for a given (seed, row).
+ * Bit-exact parity with Python's random.sample is impossible on device; the
+ * parity path feeds host-sampled index lists instead.
+ */
+int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                           const void* seeds, int seeds_is64, int64_t n_seeds, int fanout,
+                           uint64_t rng_seed, int32_t* out_row_ptr, int32_t* out_col,
+                           void* stream);
+
+/* ------------------------------------------------------------ legacy ABI -- */
+
+/*
+ * Same symbols and argument lists as dgll/FusedKernel/gcn_fused_kernel.cu:190-195
+ * and :238-244.  Semantics: H = relu(A_hat (X W)) and its TRUE gradients
+ * (the reference backward is numerically wrong):
+ *   grad_W += (A_hat X)^T (G*mask), grad_X += A_hat^T ((G*mask) W^T), mask = H>0,
+ * accumulated into the caller-zeroed buffers as gcn_extension.cpp:84-85 expects.
+ * Differences kept on purpose: launches go to the legacy default stream and the
+ * call blocks until completion (as the reference does with cudaDeviceSynchronize),
+ * but errors are reported on stderr + dgllb_last_error instead of exit(1).
+ * row_ptr is taken as authoritative (num_neighbors[i] is honoured as
+ * min(num_neighbors[i], row_ptr[i+1]-row_ptr[i]) exactly like the guard at .cu:42).
+ */
+void launch_gcn_fused_kernel(const int* row_ptr, const int* col_idx, const float* values,
+                             const float* X, const float* W, float* H,
+                             const int* num_neighbors, int N, int F_padded, int actual_F,
+                             int H_dim, int total_nnz);
+void launch_gcn_fused_kernel_backward_optimized(
+    const int* row_ptr, const int* col_idx, const float* values, const float* X,
+    const float* W, const float* grad_output, float* grad_W, float* grad_X,
+    const int* num_neighbors, int N, int F_padded, int actual_F, int H_dim, int total_nnz);
+
+/* v2 of the above: stream-ordered, non-blocking, returns a status.
+ * `H` (forward output) is required by the backward for the ReLU mask. */
+int dgllb_gcn_fused_forward(const int* row_ptr, const int* col_idx, const float* values,
+                            const float* X, const float* W, float* H,
+                            const int* num_neighbors, int N, int F_padded, int actual_F,
+                            int H_dim, int total_nnz, void* stream);
+int dgllb_gcn_fused_backward(const int* row_ptr, const int* col_idx, const float* values,
+                             const float* X, const float* W, const float* H,
+                             const float* grad_output, float* grad_W, float* grad_X,
+                             const int* num_neighbors, int N, int F_padded, int actual_F,
+                             int H_dim, int total_nnz, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGLL_B200_H_ */
