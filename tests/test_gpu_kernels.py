@@ -1,0 +1,519 @@
+"""GPU parity tests proper: every kernel is called through the C ABI (ctypes) and compared with the CPU oracle
+on the same seeded inputs.  Tolerances (BASELINE.json north_star): bit-exact for integer / byte / index work,
+<= 1e-5 relative (fp32) and <= 1e-2 (bf16) for aggregated features."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import samplers as S
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def K():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from dgll_b200 import kernels
+    return kernels
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rand_csr(rng, n_dst, n_src, max_deg, heavy=(), empty_frac=0.1, sort_cols=False):
+    deg = rng.integers(1, max_deg + 1, size=n_dst)
+    deg[rng.random(n_dst) < empty_frac] = 0
+    for r, d in heavy:
+        deg[r] = d
+    rp = np.zeros(n_dst + 1, dtype=np.int64)
+    rp[1:] = np.cumsum(deg)
+    col = rng.integers(0, n_src, size=int(rp[-1])).astype(np.int32)
+    if sort_cols:
+        for i in range(n_dst):
+            col[rp[i]:rp[i + 1]].sort()
+    return rp, col
+
+
+def padded(x, ld):
+    t = torch.zeros((x.shape[0], ld), dtype=torch.float32, device="cuda")
+    t[:, :x.shape[1]] = dev(x)
+    return t
+
+
+# ---------------------------------------------------------------- SpMM ------
+@pytest.mark.parametrize("F,ld", [(602, 604), (602, 602), (256, 256), (64, 64), (50, 52), (100, 100), (7, 7),
+                                  (128, 128), (1, 1), (33, 36)])
+@pytest.mark.parametrize("reduce", ["sum", "mean", "max"])
+def test_spmm_reduce_parity(K, F, ld, reduce):
+    rng = np.random.default_rng(F * 7 + len(reduce))
+    n_dst, n_src = 700, 1500
+    rp, col = rand_csr(rng, n_dst, n_src, 60, heavy=[(3, 900)])
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    vals = rng.random(col.size).astype(np.float32) + 0.1
+    tx = padded(x, ld)
+    for v in (None, vals):
+        ref = oracle.spmm_csr(rp, col, x, values=v, reduce=reduce)
+        out = K.spmm_csr(dev(rp), dev(col), tx, values=None if v is None else dev(v), reduce=reduce, F=F)
+        assert out.shape == (n_dst, F)
+        assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+
+
+def test_spmm_int32_rowptr_and_epilogue(K):
+    rng = np.random.default_rng(11)
+    n_dst, n_src, F = 513, 900, 96
+    rp, col = rand_csr(rng, n_dst, n_src, 30)
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    vals = rng.standard_normal(col.size).astype(np.float32)
+    rs = rng.random(n_dst).astype(np.float32)
+    add = rng.standard_normal((n_dst, F)).astype(np.float32)
+    bias = rng.standard_normal(F).astype(np.float32)
+    for relu, elu in ((True, False), (False, True), (False, False)):
+        ref = oracle.spmm_csr(rp, col, x, values=vals, reduce="sum", row_scale=rs, addend=add, bias=bias,
+                              relu=relu, elu=elu)
+        out = K.spmm_csr(dev(rp.astype(np.int32)), dev(col), dev(x), values=dev(vals), reduce="sum",
+                         row_scale=dev(rs), addend=dev(add), bias=dev(bias), relu=relu, elu=elu)
+        assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+
+
+def test_spmm_max_argmax_and_backward(K):
+    rng = np.random.default_rng(5)
+    n_dst, n_src, F = 300, 500, 40
+    rp, col = rand_csr(rng, n_dst, n_src, 25)
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    ref, ref_am = oracle.spmm_csr(rp, col, x, reduce="max", return_argmax=True)
+    out, am = K.spmm_csr(dev(rp), dev(col), dev(x), reduce="max", return_argmax=True)
+    assert np.array_equal(out.cpu().numpy(), ref)  # max of copies is exact
+    am = am.cpu().numpy()
+    assert np.array_equal(am, ref_am)
+    g = rng.standard_normal((n_dst, F)).astype(np.float32)
+    gx = K.spmm_max_backward(dev(col), dev(am), dev(g), n_src).cpu().numpy()
+    ref_gx = np.zeros((n_src, F), dtype=np.float64)
+    for i in range(n_dst):
+        for f in range(F):
+            if ref_am[i, f] >= 0:
+                ref_gx[col[ref_am[i, f]], f] += g[i, f]
+    assert rel_err(gx, ref_gx) <= FP32_TOL
+
+
+@pytest.mark.parametrize("chunk", [64, 256])
+def test_spmm_plan_heavy_rows(K, chunk):
+    rng = np.random.default_rng(chunk)
+    n_dst, n_src, F = 400, 3000, 200
+    rp, col = rand_csr(rng, n_dst, n_src, 40, heavy=[(0, 5000), (17, 777), (399, 2049)])
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    vals = rng.random(col.size).astype(np.float32)
+    bias = rng.standard_normal(F).astype(np.float32)
+    plan = K.CsrPlan(dev(rp), chunk_edges=chunk)
+    deg = rp[1:] - rp[:-1]
+    assert plan.n_heavy_rows == int((deg > chunk).sum())
+    assert plan.n_chunks == int(sum((d + chunk - 1) // chunk for d in deg if d > chunk))
+    for reduce in ("sum", "mean"):
+        ref = oracle.spmm_csr(rp, col, x, values=vals, reduce=reduce, bias=bias, relu=True)
+        out = K.spmm_csr(dev(rp), dev(col), dev(x), values=dev(vals), reduce=reduce, bias=dev(bias), relu=True,
+                         plan=plan)
+        assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+
+
+def test_spmm_bf16_features(K):
+    rng = np.random.default_rng(2)
+    n_dst, n_src, F = 600, 1000, 608
+    rp, col = rand_csr(rng, n_dst, n_src, 50)
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    xb = dev(x).to(torch.bfloat16)
+    ref_exact = oracle.spmm_csr(rp, col, xb.float().cpu().numpy(), reduce="mean")
+    out = K.spmm_csr(dev(rp), dev(col), xb, reduce="mean")
+    # same bf16-rounded inputs, fp32 accumulate: matches to fp32 tolerance ...
+    assert rel_err(out.cpu().numpy(), ref_exact) <= FP32_TOL
+    # ... and the fp32 oracle to the bf16 tolerance of north_star
+    assert rel_err(out.cpu().numpy(), oracle.spmm_csr(rp, col, x, reduce="mean")) <= BF16_TOL
+
+
+def test_spmm_segment_reduce_pooling(K):
+    """col_idx=None: scatter()-style pooling over a sorted batch vector (GlobalPooling/Pooling.py:18-81)."""
+    from oracle import layers as L
+    rng = np.random.default_rng(9)
+    sizes = rng.integers(0, 50, size=40)
+    batch = np.repeat(np.arange(40), sizes)
+    x = rng.standard_normal((batch.size, 24)).astype(np.float32)
+    rp = np.zeros(41, dtype=np.int64)
+    rp[1:] = np.cumsum(sizes)
+    for red in ("sum", "mean", "max"):
+        ref = L.pooling(torch.from_numpy(x).double(), torch.from_numpy(batch), size=40, reduce=red).numpy()
+        out = K.spmm_csr(dev(rp), None, dev(x), reduce=red).cpu().numpy()
+        assert rel_err(out, ref) <= FP32_TOL
+
+
+def test_spmm_empty_and_ragged(K):
+    x = torch.randn(10, 8, device="cuda")
+    rp = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = K.spmm_csr(rp, torch.zeros(0, dtype=torch.int32, device="cuda"), x)
+    assert out.shape == (0, 8)
+    rp = torch.zeros(6, dtype=torch.int64, device="cuda")  # 5 rows, no edges
+    out = K.spmm_csr(rp, torch.zeros(0, dtype=torch.int32, device="cuda"), x, reduce="mean")
+    assert torch.count_nonzero(out).item() == 0
+    out = K.spmm_csr(rp, torch.zeros(0, dtype=torch.int32, device="cuda"), x, reduce="max")
+    assert torch.count_nonzero(out).item() == 0
+
+
+def test_spmm_linearity_large(K):
+    """Size-independent property at a larger size: A(x+y) = Ax + Ay and mean of ones = 1 on non-empty rows."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n, F, deg = 50000, 256, 32
+    col = torch.randint(0, n, (n * deg,), device="cuda", generator=g, dtype=torch.int32)
+    rp = torch.arange(0, n * deg + 1, deg, device="cuda", dtype=torch.int64)
+    x = torch.randn(n, F, device="cuda", generator=g)
+    y = torch.randn(n, F, device="cuda", generator=g)
+    a = K.spmm_csr(rp, col, x + y)
+    b = K.spmm_csr(rp, col, x) + K.spmm_csr(rp, col, y)
+    assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item()
+    ones = K.spmm_csr(rp, col, torch.ones(n, F, device="cuda"), reduce="mean")
+    assert torch.equal(ones, torch.ones_like(ones))
+
+
+# ---------------------------------------------------------------- SDDMM -----
+@pytest.mark.parametrize("F", [64, 100, 7, 256])
+def test_sddmm_parity(K, F):
+    rng = np.random.default_rng(F)
+    n = 400
+    rp, col = rand_csr(rng, n, n, 20)
+    a = rng.standard_normal((n, F)).astype(np.float32)
+    b = rng.standard_normal((n, F)).astype(np.float32)
+    ref = oracle.sddmm_csr(rp, col, a, b)
+    out = K.sddmm_csr(dev(rp), dev(col), dev(a), dev(b)).cpu().numpy()
+    assert rel_err(out, ref) <= FP32_TOL
+
+
+# --------------------------------------------------------------- gather -----
+@pytest.mark.parametrize("F,ld,dtype", [(602, 604, np.float32), (602, 602, np.float32), (128, 128, np.float32),
+                                        (1, 1, np.float32), (2000, 2000, np.float32), (19, 20, np.int32),
+                                        (3, 3, np.uint8), (304, 304, np.float16)])
+@pytest.mark.parametrize("ids64", [True, False])
+def test_gather_rows_bit_exact(K, F, ld, dtype, ids64):
+    rng = np.random.default_rng(F)
+    n_src, m = 3000, 5001
+    if np.issubdtype(dtype, np.floating):
+        x = rng.standard_normal((n_src, ld)).astype(dtype)
+    else:
+        x = rng.integers(0, 200, size=(n_src, ld)).astype(dtype)
+    ids = rng.integers(0, n_src, size=m).astype(np.int64 if ids64 else np.int32)
+    table = dev(x)
+    view = table[:, :F]
+    ref, _ = oracle.gather_rows(np.ascontiguousarray(x[:, :F]), ids)
+    out = K.gather_rows(view, dev(ids))
+    assert out.dtype == table.dtype and out.shape == (m, F)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_gather_rows_empty_and_1d(K):
+    table = torch.arange(100, device="cuda", dtype=torch.int64)
+    ids = torch.tensor([5, 0, 99, 5], device="cuda")
+    assert K.gather_rows(table, ids).tolist() == [5, 0, 99, 5]
+    out = K.gather_rows(torch.randn(10, 16, device="cuda"), torch.zeros(0, dtype=torch.int64, device="cuda"))
+    assert out.shape == (0, 16)
+
+
+def test_gather_rows_cached_split(K):
+    """GraphCacheServer.fetch_data semantics (FeatureCache/storage.py:151-198): hits from the HBM cache, misses
+    from the pinned host table, miss counter — against the oracle's restatement."""
+    rng = np.random.default_rng(3)
+    n, F, m = 2000, 604, 3333
+    host = rng.standard_normal((n, F)).astype(np.float32)
+    deg = rng.integers(0, 1000, size=n)
+    cached = np.argsort(-deg, kind="stable")[:700]
+    flag = np.zeros(n, dtype=np.uint8)
+    flag[cached] = 1
+    l2c = np.zeros(n, dtype=np.int64)
+    l2c[cached] = np.arange(cached.size)
+    cache = host[cached].copy()
+    ids = rng.integers(0, n, size=m).astype(np.int64)
+    ref, ref_miss = oracle.gather_rows(cache, ids, host_table=host, gpu_flag=flag, local2cache=l2c)
+    assert np.array_equal(ref, host[ids])
+    host_t = torch.from_numpy(host).pin_memory()
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = K.gather_rows_cached(dev(cache), host_t, dev(ids), dev(flag), dev(l2c), miss_counter=counter)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert int(counter.item()) == ref_miss == int((flag[ids] == 0).sum())
+
+
+# ------------------------------------------------------------ binarized -----
+@pytest.mark.parametrize("F", [602, 32, 33, 128, 1, 1000])
+def test_binarize_and_bin_spmm_bit_exact(K, F):
+    rng = np.random.default_rng(F)
+    n_dst, n_src = 500, 1200
+    rp, col = rand_csr(rng, n_dst, n_src, 70, heavy=[(1, 1500)])
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    x[rng.random(x.shape) < 0.05] = 0.0   # exact zeros count as +1 (x >= 0)
+    x[0, 0] = -0.0                        # -0.0 >= 0 is true
+    packed = K.binarize_pack(dev(x))
+    ref_packed = oracle.binarize_pack(x)
+    assert np.array_equal(packed.cpu().numpy().view(np.uint32), ref_packed)
+    ref_cnt = oracle.bin_spmm_counts(rp, col, ref_packed, F)
+    cnt = K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="count").cpu().numpy()
+    assert cnt.dtype == np.int32 and np.array_equal(cnt, ref_cnt)
+    deg = (rp[1:] - rp[:-1]).astype(np.float32)[:, None]
+    s = K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="sum").cpu().numpy()
+    assert np.array_equal(s, 2.0 * ref_cnt.astype(np.float32) - deg)
+    m = K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="mean").cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref_m = np.where(deg > 0, (2.0 * ref_cnt - deg) / deg, 0.0)
+    assert rel_err(m, ref_m) <= FP32_TOL
+    # cross-check with the fp32 kernel on sign(x): same aggregation, different formulation
+    sx = np.where(x >= 0, 1.0, -1.0).astype(np.float32)
+    agg = K.spmm_csr(dev(rp), dev(col), dev(sx), reduce="sum").cpu().numpy()
+    assert np.array_equal(agg, s)
+
+
+# ------------------------------------------------------------------ GAT -----
+@pytest.mark.parametrize("heads,D", [(4, 64), (1, 47), (4, 16), (2, 8), (1, 256), (3, 5)])
+@pytest.mark.parametrize("mode", ["softmax", "exp_neg"])
+def test_gat_forward_parity(K, heads, D, mode):
+    rng = np.random.default_rng(heads * 100 + D)
+    n = 600
+    rp, col = rand_csr(rng, n, n, 40, heavy=[(2, 700)])
+    wh = rng.standard_normal((n, heads * D)).astype(np.float32)
+    el = rng.standard_normal((n, heads)).astype(np.float32)
+    er = rng.standard_normal((n, heads)).astype(np.float32)
+    for elu in (False, True):
+        ref = oracle.gat_forward(rp, col, wh, el, er, heads, 0.2, mode=mode, elu=elu)
+        out = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, elu=elu)
+        assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+
+
+@pytest.mark.parametrize("heads,D", [(4, 64), (1, 47), (2, 8)])
+@pytest.mark.parametrize("mode", ["softmax", "exp_neg"])
+def test_gat_backward_matches_autograd(K, heads, D, mode):
+    rng = np.random.default_rng(heads + D)
+    n = 300
+    rp, col = rand_csr(rng, n, n, 20)
+    wh = rng.standard_normal((n, heads * D)).astype(np.float32)
+    el = rng.standard_normal((n, heads)).astype(np.float32)
+    er = rng.standard_normal((n, heads)).astype(np.float32)
+    g = rng.standard_normal((n, heads * D)).astype(np.float32)
+    # fp64 autograd reference of the same definition (oracle/layers.py restates gatconv.py; here per-edge form)
+    rows = torch.from_numpy(np.repeat(np.arange(n), rp[1:] - rp[:-1])).long()
+    cols = torch.from_numpy(col).long()
+    twh = torch.from_numpy(wh).double().requires_grad_(True)
+    tel = torch.from_numpy(el).double().requires_grad_(True)
+    ter = torch.from_numpy(er).double().requires_grad_(True)
+    z = torch.nn.functional.leaky_relu(tel[rows] + ter[cols], 0.2)
+    s = z if mode == "softmax" else -z
+    smax = torch.full((n, heads), -float("inf"), dtype=torch.float64).scatter_reduce(
+        0, rows[:, None].expand(-1, heads), s.detach(), reduce="amax")
+    ex = torch.exp(s - smax[rows])
+    den = torch.zeros(n, heads, dtype=torch.float64).index_add_(0, rows, ex)
+    alpha = ex / den[rows]
+    msg = alpha[:, :, None] * twh[cols].view(-1, heads, D)
+    out_ref = torch.zeros(n, heads, D, dtype=torch.float64).index_add_(0, rows, msg).view(n, heads * D)
+    out_ref.backward(torch.from_numpy(g).double())
+
+    drp, dcol = dev(rp), dev(col)
+    out, rmax, rsum = K.gat_forward(drp, dcol, dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, save_stats=True)
+    assert rel_err(out.cpu().numpy(), out_ref.detach().numpy()) <= FP32_TOL
+    trp, tcol, _, perm = K.csr_transpose(drp, dcol, n, want_perm=True)
+    d_wh, d_el, d_er = K.gat_backward(drp, dcol, trp, tcol, perm, dev(wh), dev(el), dev(er), out, rmax, rsum,
+                                      dev(g), heads, 0.2, mode=mode)
+    assert rel_err(d_wh.cpu().numpy(), twh.grad.numpy()) <= 2e-5
+    assert rel_err(d_el.cpu().numpy(), tel.grad.numpy()) <= 2e-5
+    assert rel_err(d_er.cpu().numpy(), ter.grad.numpy()) <= 2e-5
+
+
+# ------------------------------------------------------------ transpose -----
+def test_csr_transpose_bit_exact(K):
+    rng = np.random.default_rng(4)
+    n_rows, n_cols = 700, 500
+    rp, col = rand_csr(rng, n_rows, n_cols, 30)
+    vals = rng.standard_normal(col.size).astype(np.float32)
+    for rpt in (np.int64, np.int32):
+        t_rp, t_col, t_val, perm = K.csr_transpose(dev(rp.astype(rpt)), dev(col), n_cols, values=dev(vals),
+                                                   want_perm=True)
+        rows = np.repeat(np.arange(n_rows), rp[1:] - rp[:-1])
+        order = np.argsort(col, kind="stable")
+        ref_rp = np.zeros(n_cols + 1, dtype=np.int64)
+        np.add.at(ref_rp, col.astype(np.int64) + 1, 1)
+        ref_rp = np.cumsum(ref_rp)
+        assert np.array_equal(t_rp.cpu().numpy(), ref_rp)
+        assert np.array_equal(t_col.cpu().numpy(), rows[order])
+        assert np.array_equal(perm.cpu().numpy(), order)
+        assert np.array_equal(t_val.cpu().numpy(), vals[order])
+
+
+# ----------------------------------------------------------------- GEMM -----
+@pytest.mark.parametrize("M,N,K_", [(300, 64, 50), (1000, 256, 602), (17, 5, 3), (128, 121, 64)])
+def test_gemm_fp32_parity(K, M, N, K_):
+    rng = np.random.default_rng(M)
+    a = rng.standard_normal((M, K_)).astype(np.float32)
+    b = rng.standard_normal((K_, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = oracle.gemm(a, b, bias=bias, relu=True)
+    out = K.gemm(dev(a), dev(b), bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(out, ref) <= FP32_TOL
+    # transposed operands + accumulate (dW = H^T G)
+    g = rng.standard_normal((M, N)).astype(np.float32)
+    acc = rng.standard_normal((K_, N)).astype(np.float32)
+    ref2 = acc.astype(np.float64) + a.astype(np.float64).T @ g.astype(np.float64)
+    o = dev(acc)
+    K.gemm(dev(a), dev(g), trans_a=True, out=o, accumulate=True)
+    assert rel_err(o.cpu().numpy(), ref2) <= FP32_TOL
+    ref3 = g.astype(np.float64) @ b.astype(np.float64).T
+    assert rel_err(K.gemm(dev(g), dev(b), trans_b=True).cpu().numpy(), ref3) <= FP32_TOL
+
+
+# -------------------------------------------------------------- sampler -----
+@pytest.mark.parametrize("fanout", [10, 25, 1, 32, -1])
+def test_sample_neighbors_structure(K, fanout):
+    rng = np.random.default_rng(8)
+    n = 2000
+    rp, col = rand_csr(rng, n, n, 80, empty_frac=0.05)
+    # distinct neighbours per row so "no duplicates" is checkable
+    for i in range(n):
+        d = rp[i + 1] - rp[i]
+        col[rp[i]:rp[i + 1]] = rng.choice(n, size=d, replace=False)
+    seeds = rng.integers(0, n, size=1024).astype(np.int64)
+    o_rp, o_col = K.sample_neighbors(dev(rp), dev(col), dev(seeds), fanout, rng_seed=123)
+    o_rp, o_col = o_rp.cpu().numpy(), o_col.cpu().numpy()
+    deg = (rp[1:] - rp[:-1])[seeds]
+    want = deg if fanout < 0 else np.minimum(deg, fanout)
+    assert np.array_equal(np.diff(o_rp), want) and o_rp[0] == 0
+    for i, v in enumerate(seeds):
+        got = o_col[o_rp[i]:o_rp[i + 1]]
+        nb = col[rp[v]:rp[v + 1]]
+        if fanout < 0 or deg[i] <= fanout:
+            assert np.array_equal(got, nb)  # all neighbours, original order (base_sampler.py:53-54)
+        else:
+            assert len(set(got.tolist())) == len(got)          # without replacement
+            assert set(got.tolist()) <= set(nb.tolist())       # subset of the neighbourhood
+            pos = [int(np.where(nb == g_)[0][0]) for g_ in got]
+            assert pos == sorted(pos)                          # neighbour order kept
+    # determinism for a given rng_seed, different draw for another
+    o2 = K.sample_neighbors(dev(rp), dev(col), dev(seeds), fanout, rng_seed=123)[1].cpu().numpy()
+    assert np.array_equal(o2, o_col)
+    if fanout in (10, 25):
+        o3 = K.sample_neighbors(dev(rp), dev(col), dev(seeds), fanout, rng_seed=124)[1].cpu().numpy()
+        assert not np.array_equal(o3, o_col)
+
+
+def test_sample_neighbors_uniformity(K):
+    """Every neighbour of a degree-50 node is chosen with probability fanout/deg (chi-square-ish bound)."""
+    deg, fanout, trials = 50, 10, 20000
+    rp = np.array([0, deg], dtype=np.int64)
+    col = np.arange(deg, dtype=np.int32)
+    seeds = np.zeros(trials, dtype=np.int64)
+    _, o_col = K.sample_neighbors(dev(rp), dev(col), dev(seeds), fanout, rng_seed=7)
+    hist = np.bincount(o_col.cpu().numpy(), minlength=deg)
+    expect = trials * fanout / deg
+    assert np.all(np.abs(hist - expect) < 6 * np.sqrt(expect))
+
+
+def test_host_sampled_blocks_aggregate_exactly(K):
+    """Parity protocol of SURVEY.md App. B: the reference's host sampler (restated) produces the index lists; the
+    device aggregates them; result equals the oracle on the same lists."""
+    import random
+    rng = np.random.default_rng(21)
+    n, F = 500, 602
+    rp, col = rand_csr(rng, n, n, 30)
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    seeds = list(range(0, 64))
+    random.seed(0)
+    src, dst = S.sample_neighbours(rp, col, seeds, 10, rng=random)
+    b_rp = S.block_to_csr(dst, seeds)
+    b_rp = np.asarray(b_rp, dtype=np.int64)
+    b_col = np.asarray(src, dtype=np.int32)
+    ref = oracle.spmm_csr(b_rp, b_col, x, reduce="mean")
+    out = K.spmm_csr(dev(b_rp), dev(b_col), padded(x, 604), reduce="mean", F=F).cpu().numpy()
+    assert rel_err(out, ref) <= FP32_TOL
+
+
+# ---------------------------------------------------------- legacy fused ----
+def _fused_inputs(rng, N, F, Hd):
+    rp, col = rand_csr(rng, N, N, 25, empty_frac=0.05)
+    vals = (rng.random(col.size).astype(np.float32) + 0.05) / 10
+    Fp = (F + 3) // 4 * 4
+    X = np.zeros((N, Fp), dtype=np.float32)
+    X[:, :F] = rng.standard_normal((N, F)).astype(np.float32)
+    W = (rng.standard_normal((Fp, Hd)) / np.sqrt(F)).astype(np.float32)
+    nn = (rp[1:] - rp[:-1]).astype(np.int32)
+    return rp.astype(np.int32), col, vals, X, W, nn, Fp
+
+
+@pytest.mark.parametrize("N,F,Hd", [(591, 50, 64), (1021, 64, 121), (300, 602, 41)])
+def test_gcn_fused_forward_backward(K, N, F, Hd):
+    rng = np.random.default_rng(N)
+    rp, col, vals, X, W, nn, Fp = _fused_inputs(rng, N, F, Hd)
+    ref = oracle.gcn_fused_forward(rp, col, vals, X, W, nn, F)
+    H = K.gcn_fused_forward_v2(dev(rp), dev(col), dev(vals), dev(X), dev(W), dev(nn), F)
+    assert rel_err(H.cpu().numpy(), ref) <= FP32_TOL
+    # true gradients: torch autograd over relu(A (X W)) in fp64
+    rows = torch.from_numpy(np.repeat(np.arange(N), np.diff(rp))).long()
+    A = torch.sparse_coo_tensor(torch.stack([rows, torch.from_numpy(col).long()]),
+                                torch.from_numpy(vals).double(), (N, N))
+    tX = torch.from_numpy(X).double().requires_grad_(True)
+    tW = torch.from_numpy(W).double().requires_grad_(True)
+    Wm = tW.clone()
+    out = torch.relu(torch.sparse.mm(A, tX[:, :F] @ Wm[:F]))
+    g = rng.standard_normal((N, Hd)).astype(np.float32)
+    out.backward(torch.from_numpy(g).double())
+    gX, gW = K.gcn_fused_backward_v2(dev(g), dev(rp), dev(col), dev(vals), dev(X), dev(W), H, dev(nn), F)
+    assert rel_err(gX.cpu().numpy()[:, :F], tX.grad.numpy()[:, :F]) <= 2e-5
+    assert rel_err(gW.cpu().numpy()[:F], tW.grad.numpy()[:F]) <= 2e-5
+
+
+def test_legacy_symbols_blocking_abi(K):
+    """launch_gcn_fused_kernel keeps the reference's C ABI (gcn_fused_kernel.cu:190-195): void, blocking."""
+    import ctypes
+    from dgll_b200 import _lib
+    rng = np.random.default_rng(1)
+    N, F, Hd = 400, 50, 64
+    rp, col, vals, X, W, nn, Fp = _fused_inputs(rng, N, F, Hd)
+    t = [dev(a) for a in (rp, col, vals, X, W, nn)]
+    H = torch.zeros((N, Hd), device="cuda")
+    torch.cuda.synchronize()
+    P = lambda z: ctypes.c_void_p(z.data_ptr())
+    _lib.lib().launch_gcn_fused_kernel(P(t[0]), P(t[1]), P(t[2]), P(t[3]), P(t[4]), P(H), P(t[5]), N, Fp, F, Hd,
+                                       col.size)
+    ref = oracle.gcn_fused_forward(rp, col, vals, X, W, nn, F)
+    assert rel_err(H.cpu().numpy(), ref) <= FP32_TOL
+
+
+def test_reference_kernel_agrees_with_oracle_when_built(K):
+    """oracle/_ref holds the reference's own forward kernel compiled for sm_100a (when it was built in the
+    container that has /root/reference): the restated oracle must match it on PPI-like shapes."""
+    import ctypes
+    path = oracle.ref_kernel_path()
+    if path is None:
+        pytest.skip("oracle/_ref/libgcn_fused_ref.so not built")
+    ref_lib = ctypes.CDLL(path)
+    rng = np.random.default_rng(6)
+    N, F, Hd = 591, 50, 64
+    rp, col, vals, X, W, nn, Fp = _fused_inputs(rng, N, F, Hd)
+    t = [dev(a) for a in (rp, col, vals, X, W, nn)]
+    H = torch.zeros((N, Hd), device="cuda")
+    torch.cuda.synchronize()
+    P = lambda z: ctypes.c_void_p(z.data_ptr())
+    ref_lib.launch_gcn_fused_kernel.restype = None
+    ref_lib.launch_gcn_fused_kernel(P(t[0]), P(t[1]), P(t[2]), P(t[3]), P(t[4]), P(H), P(t[5]), ctypes.c_int(N),
+                                    ctypes.c_int(Fp), ctypes.c_int(F), ctypes.c_int(Hd), ctypes.c_int(col.size))
+    torch.cuda.synchronize()
+    orc = oracle.gcn_fused_forward(rp, col, vals, X, W, nn, F)
+    assert rel_err(H.cpu().numpy(), orc) <= FP32_TOL
+    ours = K.gcn_fused_forward_v2(*t[:5], t[5], F)
+    assert rel_err(ours.cpu().numpy(), H.cpu().numpy()) <= FP32_TOL
+
+
+def test_ppi_golden_layer_on_device(K):
+    """C1: the reference's PPI GCNLayer output (golden, generated from Evaluation/PPI/gcn_model.py) reproduced by
+    GEMM + SpMM(sum, relu) on the device."""
+    from conftest import golden
+    g = golden("ppi_gcn_g8")
+    ei = g["edge_index"]
+    n = g["feats"].shape[0]
+    rp, col, _ = oracle.coo_to_csr(ei[0], ei[1], n)
+    support = K.gemm(dev(g["feats"].astype(np.float32)), dev(g["w0"].astype(np.float32)))
+    h1 = K.spmm_csr(dev(rp), dev(col), support, reduce="sum", relu=True)
+    assert rel_err(h1.cpu().numpy(), g["h1"]) <= FP32_TOL
