@@ -220,7 +220,8 @@ def main():
     # ---- synthetic inputs, resident in HBM -------------------------------------------------------------
     t_setup = time.perf_counter()
     row_ptr, col_idx = G.rmat_csr(N_NODES, NNZ, seed=args.seed, device=dev)
-    table = G.feature_table(N_NODES, FEAT, seed=args.seed, device=dev)        # [N, 604] fp32, 563 MB > L2
+    LD = int(os.environ.get("BENCH_LD", "604"))
+    table = G.feature_table(N_NODES, FEAT, seed=args.seed, device=dev, pad_to=LD)  # [N, 604] fp32, 563 MB > L2
     gen = torch.Generator(device=dev).manual_seed(args.seed + 1000 * rank)
     n_train = int(0.66 * N_NODES)
     perm = torch.randperm(n_train, device=dev, generator=gen)
@@ -232,7 +233,7 @@ def main():
         batches.append({
             "rp0": b0.row_ptr, "col0": b0.col_global, "dst0": b0.dst_ids.contiguous(), "n_dst0": b0.num_dst,
             "rp1": b1.row_ptr, "col1": b1.col, "n_dst1": b1.num_dst,
-            "agg0": torch.empty((b0.num_dst, FEAT), device=dev), "self0": torch.empty((b0.num_dst, 604), device=dev),
+            "agg0": torch.empty((b0.num_dst, FEAT), device=dev), "self0": torch.empty((b0.num_dst, LD), device=dev),
             "agg1": torch.empty((b1.num_dst, HIDDEN), device=dev),
             "h1": torch.randn((b0.num_dst, HIDDEN), device=dev, generator=gen),
         })

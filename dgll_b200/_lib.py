@@ -30,7 +30,7 @@ SIGNATURES = {
     "dgllb_csr_plan_create": (_I, [_P, _I, _L, _I, _P, POINTER(c_void_p)]),
     "dgllb_csr_plan_info": (_I, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
     "dgllb_csr_plan_destroy": (None, [_P]),
-    "dgllb_spmm_csr": (_I, [_P, _I, _P, _P, _P, _I, _L, _P, _L, _L, _L, _I, _I, _P, _P, _L, _P, _I, _P, _P, _P]),
+    "dgllb_spmm_csr": (_I, [_P, _I, _P, _P, _P, _I, _L, _P, _L, _L, _L, _L, _I, _I, _P, _P, _L, _P, _I, _P, _P, _P]),
     "dgllb_sddmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _P, _L, _I, _P]),
     "dgllb_spmm_max_backward": (_I, [_P, _P, _P, _L, _P, _L, _L, _I, _P]),
     "dgllb_csr_transpose": (_I, [_P, _I, _P, _P, _L, _L, _L, _P, _P, _P, _P, _P]),

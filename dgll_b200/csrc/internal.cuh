@@ -29,10 +29,15 @@ struct SpmmParams {
     long long n_heavy_items;
     int chunk_edges;          // 0 = no plan
     const int* row_cnt;       // optional per-row edge-count clamp (legacy num_neighbors)
+    long long nnz_hint;       // host-known upper bound on row_ptr[n_dst]; < 0 = unknown
+    int out_vec;              // out rows are 16-byte aligned: 128-bit stores / RED.ADD.128 allowed
 };
 
 // run the aggregation kernel(s) for a filled parameter block (spmm.cu)
 int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan, cudaStream_t st);
+
+// TMA-staged aggregation (spmm_bulk.cu); DGLLB_ERR_UNSUPPORTED = shape not taken, caller falls through
+int spmm_bulk_try(const SpmmParams& p, int x_dtype, long long nnz, cudaStream_t st);
 
 // exact-fp32 SIMT GEMM (gemm_simt.cu)
 int gemm_simt(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,

@@ -44,6 +44,8 @@ static SpmmParams make_params(const int* row_ptr, const int* col, const float* v
     p.row_scale = nullptr; p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.epi = epi;
     p.argmax = nullptr; p.heavy_items = nullptr; p.n_heavy_items = 0; p.chunk_edges = 0;
     p.row_cnt = row_cnt;
+    p.nnz_hint = -1;
+    p.out_vec = 0;
     return p;
 }
 

@@ -21,9 +21,9 @@
 // Algorithmic bytes per launch: nnz*(4 + [4 values] + F*b) + n_dst*(F*4 + r).
 #include "common.cuh"
 #include "internal.cuh"
+#include <stdlib.h>
 
 namespace dgllb {
-
 
 __device__ __forceinline__ long long load_rp(const void* p, int is64, long long i) {
     return is64 ? reinterpret_cast<const long long*>(p)[i]
@@ -88,6 +88,36 @@ struct RowLoad<__nv_bfloat16, 1> {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 8;
+
+// scale / addend / bias / activation / store of one finished row piece (A consecutive columns at col0)
+template <int A>
+__device__ __forceinline__ void store_row(const SpmmParams& p, long long row, int col0, float* acc, long long deg) {
+    float scale = 1.f;
+    if (p.mean) scale = deg > 0 ? 1.f / static_cast<float>(deg) : 0.f;
+    if (p.row_scale) scale *= __ldg(p.row_scale + row);
+    float* __restrict__ o = p.out + row * p.ldo + col0;
+    const int valid = min(A, p.F - col0);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        float v = acc[a] * scale;
+        if (a < valid) {
+            if (p.addend) v += __ldg(p.addend + row * p.ld_add + col0 + a);
+            if (p.bias) v += __ldg(p.bias + col0 + a);
+            v = apply_epi(v, p.epi);
+        }
+        acc[a] = v;
+    }
+    if (A >= 4 && valid == A && p.out_vec) {
+#pragma unroll
+        for (int a = 0; a < A; a += 4)
+            stg_cs_f4(o + a, make_float4(acc[a], acc[a + 1], acc[a + 2], acc[a + 3]));
+    } else {
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+            if (a < valid) o[a] = acc[a];
+    }
+}
+
 
 // ------------------------------------------------------------ main kernel --
 template <typename XT, int VE, int LANES, bool IS_MAX>
@@ -210,7 +240,7 @@ spmm_rowslab_kernel(const SpmmParams p) {
     if (heavy) {
         // partial sums of a split row: combine with RED.ADD (rows were pre-zeroed);
         // epilogue runs in spmm_finalize_heavy_kernel.
-        if (A == 4 && valid == 4) {
+        if (A == 4 && valid == 4 && p.out_vec) {
             atomicAdd(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
         } else {
 #pragma unroll
@@ -229,7 +259,7 @@ spmm_rowslab_kernel(const SpmmParams p) {
             acc[a] = apply_epi(v, p.epi);
         }
     }
-    if (A >= 4 && valid == A) {
+    if (A >= 4 && valid == A && p.out_vec) {
 #pragma unroll
         for (int a = 0; a < A; a += 4)
             stg_cs_f4(o + a, make_float4(acc[a], acc[a + 1], acc[a + 2], acc[a + 3]));
@@ -243,6 +273,165 @@ spmm_rowslab_kernel(const SpmmParams p) {
 #pragma unroll
         for (int a = 0; a < A; ++a)
             if (a < valid) am[a] = amax[a];
+    }
+}
+
+// ------------------------------------------------------- streaming kernel --
+// Row-aligned nnz-split ("merge-path" by edges, boundaries snapped to row starts): warp (q, slab) owns the
+// rows whose first edge lies in [q*T, (q+1)*T) and streams their concatenated edge list with a ROLLING
+// window of kDepth source rows in flight per lane: as soon as edge j's piece is consumed, the load for edge
+// j+kDepth is issued, across row boundaries, so short rows (sampled blocks: <= fanout edges) never drain the
+// memory pipeline the way one-warp-per-row does.  Every row is owned by exactly one warp: no atomics,
+// deterministic, fp32 accumulation in CSR edge order.  Column indices (and edge values) are fetched 32 at a
+// time, one chunk ahead, and broadcast with shuffles; row ends travel the same way.
+constexpr int kDepth = 8;
+
+template <typename XT, int VE, bool HAS_VALS>
+__global__ void __launch_bounds__(kThreads, 3)
+spmm_stream_kernel(const SpmmParams p, const int T, const long long n_chunks) {
+    typedef RowLoad<XT, VE> L;
+    constexpr int A = L::kAcc;
+    const int lane = threadIdx.x & 31;
+    const long long wid = (static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    const long long q = wid / p.n_slabs;
+    if (q >= n_chunks) return;
+    const int slab = static_cast<int>(wid - q * p.n_slabs);
+
+    // first row whose start is >= t: even lanes search q*T, odd lanes (q+1)*T
+    long long r0, r1;
+    {
+        const long long t = (q + (lane & 1)) * static_cast<long long>(T);
+        long long lo = 0, hi = p.n_dst;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (load_rp(p.row_ptr, p.rp64, mid) < t) lo = mid + 1; else hi = mid;
+        }
+        r0 = __shfl_sync(0xffffffffu, lo, 0);
+        r1 = __shfl_sync(0xffffffffu, lo, 1);
+        if (q == n_chunks - 1) r1 = p.n_dst;
+    }
+    if (r0 >= r1) return;  // this edge range lies inside one long row owned by an earlier warp
+    const long long ebase = load_rp(p.row_ptr, p.rp64, r0);
+    const int m = static_cast<int>(load_rp(p.row_ptr, p.rp64, r1) - ebase);
+
+    const int col0 = (slab * 32 + lane) * A;
+    const bool lane_on = col0 < p.F;
+    const XT* __restrict__ Xb = reinterpret_cast<const XT*>(p.X) + col0;
+    const long long ldx = p.ldx;
+    const int* __restrict__ cb = p.col + ebase;
+    const float* __restrict__ vb = HAS_VALS ? p.vals + ebase : nullptr;
+
+    int my_c = lane < m ? __ldg(cb + lane) : 0;
+    int my_cn = 32 + lane < m ? __ldg(cb + 32 + lane) : 0;
+    float my_w = 1.f, my_wn = 1.f;
+    if (HAS_VALS) {
+        my_w = lane < m ? __ldg(vb + lane) : 0.f;
+        my_wn = 32 + lane < m ? __ldg(vb + 32 + lane) : 0.f;
+    }
+    // row-end offsets (relative to ebase) of rows row_w0 + lane; INT_MAX past the owned range
+    long long row = r0, row_w0 = r0;
+    int my_re = (row_w0 + lane < r1) ? static_cast<int>(load_rp(p.row_ptr, p.rp64, row_w0 + lane + 1) - ebase)
+                                     : 0x7fffffff;
+    int rstart = 0;
+    int rend = __shfl_sync(0xffffffffu, my_re, 0);
+
+    typename L::raw_t raw[kDepth];
+    float w[kDepth];
+#pragma unroll
+    for (int u = 0; u < kDepth; ++u) {
+        const int c = __shfl_sync(0xffffffffu, my_c, u);
+        if (HAS_VALS) w[u] = __shfl_sync(0xffffffffu, my_w, u);
+        if (lane_on && u < m) raw[u] = L::load(Xb + static_cast<long long>(c) * ldx);
+    }
+    float acc[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) acc[a] = 0.f;
+
+    // The flush inside the rolling loop stays tiny (no calls, no spills): it stores scale * sum only.  The rare
+    // epilogue terms (row_scale / addend / bias / activation) are applied by a second pass of the SAME thread
+    // over the rows it has just written (they are still in L1/L2; n_dst*F*4 B is small next to the gather).
+    const bool need_epi = p.row_scale || p.addend || p.bias || p.epi;
+    const int valid = min(A, p.F - col0);
+    const bool full_vec = p.out_vec && valid == A;
+    auto flush = [&]() {
+        if (lane_on) {
+            const int deg = rend - rstart;
+            const float scale = p.mean ? (deg > 0 ? 1.f / static_cast<float>(deg) : 0.f) : 1.f;
+            float* __restrict__ o = p.out + row * p.ldo + col0;
+            if (full_vec) {
+#pragma unroll
+                for (int a = 0; a < A; a += 4) {
+                    const float4 v4 = make_float4(acc[a] * scale, acc[a + 1] * scale, acc[a + 2] * scale,
+                                                  acc[a + 3] * scale);
+                    if (need_epi) *reinterpret_cast<float4*>(o + a) = v4; else stg_cs_f4(o + a, v4);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < A; ++a)
+                    if (a < valid) o[a] = acc[a] * scale;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a) acc[a] = 0.f;
+        rstart = rend;
+        ++row;
+        if (row - row_w0 == 32) {
+            row_w0 = row;
+            my_re = (row_w0 + lane < r1)
+                        ? static_cast<int>(load_rp(p.row_ptr, p.rp64, row_w0 + lane + 1) - ebase)
+                        : 0x7fffffff;
+        }
+        rend = __shfl_sync(0xffffffffu, my_re, static_cast<int>(row - row_w0));
+    };
+
+    for (int jb = 0; jb < m; jb += 32) {
+#pragma unroll 1
+        for (int k8 = 0; k8 < 32; k8 += kDepth) {
+            if (jb + k8 >= m) break;
+            // the refills of this group read indices kn = k8+kDepth.. : current chunk or the next one (warp-uniform)
+            const bool nxt = k8 + kDepth >= 32;
+            const int csel = nxt ? my_cn : my_c;
+            const float wsel = nxt ? my_wn : my_w;
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) {
+                const int j = jb + k8 + u;
+                while (j >= rend) flush();  // rows that ended before edge j (also empty rows)
+                if (j < m) {
+                    float v[A];
+                    L::unpack(raw[u], v);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) acc[a] = HAS_VALS ? fmaf(w[u], v[a], acc[a]) : acc[a] + v[a];
+                }
+                // refill the slot with edge j + kDepth
+                const int src = (k8 + kDepth + u) & 31;
+                const int c = __shfl_sync(0xffffffffu, csel, src);
+                if (HAS_VALS) w[u] = __shfl_sync(0xffffffffu, wsel, src);
+                if (lane_on && j + kDepth < m) raw[u] = L::load(Xb + static_cast<long long>(c) * ldx);
+            }
+        }
+        my_c = my_cn;
+        my_cn = jb + 64 + lane < m ? __ldg(cb + jb + 64 + lane) : 0;
+        if (HAS_VALS) {
+            my_w = my_wn;
+            my_wn = jb + 64 + lane < m ? __ldg(vb + jb + 64 + lane) : 0.f;
+        }
+    }
+    while (row < r1) flush();
+
+    if (need_epi && lane_on) {
+        for (long long r = r0; r < r1; ++r) {
+            float* __restrict__ o = p.out + r * p.ldo + col0;
+            const float rs = p.row_scale ? __ldg(p.row_scale + r) : 1.f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                if (a < valid) {
+                    float v = o[a] * rs;
+                    if (p.addend) v += __ldg(p.addend + r * p.ld_add + col0 + a);
+                    if (p.bias) v += __ldg(p.bias + col0 + a);
+                    o[a] = apply_epi(v, p.epi);
+                }
+            }
+        }
     }
 }
 
@@ -394,6 +583,35 @@ static int launch_spmm(const SpmmParams& p, bool is_max, cudaStream_t st) {
     return DGLLB_OK;
 }
 
+// edges per warp for the streaming kernel: enough warps for ~4 full waves, at least 32, at most 1024 edges
+static int stream_chunk_edges(long long nnz, int n_slabs, int sm_count) {
+    const long long target_warps = static_cast<long long>(sm_count) * 32 * 4;
+    long long t = (nnz * n_slabs + target_warps - 1) / target_warps;
+    t = (t + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > 1024) t = 1024;
+    return static_cast<int>(t);
+}
+
+template <typename XT, int VE>
+static int launch_spmm_stream(SpmmParams& p, long long nnz, cudaStream_t st) {
+    DevInfo di;
+    int rc = get_devinfo(&di);
+    if (rc != DGLLB_OK) return rc;
+    p.n_slabs = (p.F + 32 * VE - 1) / (32 * VE);
+    const int T = stream_chunk_edges(nnz, p.n_slabs, di.sm_count);
+    const long long n_chunks = nnz > 0 ? (nnz + T - 1) / T : 1;
+    const long long warps = n_chunks * p.n_slabs;
+    const long long blocks = (warps * 32 + kThreads - 1) / kThreads;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "spmm: grid too large (%lld blocks)", blocks);
+    if (p.vals)
+        spmm_stream_kernel<XT, VE, true><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p, T, n_chunks);
+    else
+        spmm_stream_kernel<XT, VE, false><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p, T, n_chunks);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
 template <typename XT, int VE>
 static int launch_spmm_lanes(SpmmParams& p, bool is_max, cudaStream_t st) {
     // smallest group whose slab covers F, so narrow rows do not idle lanes
@@ -422,15 +640,33 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
         DGLLB_LAUNCH_CHECK();
     }
     int rc;
+    p.out_vec = aligned16(p.out) && (p.ldo % 4 == 0);
+    // streaming kernel: sum/mean over an explicit col_idx with a host-known nnz bound, wide rows, no split plan
+    bool stream_ok = !is_max && !use_plan && p.col && !p.row_cnt && p.nnz_hint >= 0;
+    // DGLLB_SPMM_KERNEL=rowsplit|stream|bulk pins one kernel family (profiling / A-B runs); default = best available
+    const char* force = getenv("DGLLB_SPMM_KERNEL");
+    const bool want_bulk = !force || force[0] == 'b';
+    if (force && force[0] == 'r') stream_ok = false;
+    if (stream_ok && want_bulk) {
+        rc = spmm_bulk_try(p, x_dtype, p.nnz_hint, st);
+        if (rc != DGLLB_ERR_UNSUPPORTED) {
+            if (rc != DGLLB_OK) return rc;
+            goto finalize;
+        }
+    }
     if (x_dtype == DGLLB_F32) {
-        const bool vec = aligned16(p.X) && aligned16(p.out) && (p.ldx % 4 == 0) && (p.ldo % 4 == 0);
-        rc = vec ? launch_spmm_lanes<float, 4>(p, is_max, st) : launch_spmm_lanes<float, 1>(p, is_max, st);
+        // 128-bit LOADS need only the source table aligned; the output falls back to scalar stores by itself
+        const bool vec = aligned16(p.X) && (p.ldx % 4 == 0);
+        if (vec && stream_ok && p.F > 16 * 4) rc = launch_spmm_stream<float, 4>(p, p.nnz_hint, st);
+        else rc = vec ? launch_spmm_lanes<float, 4>(p, is_max, st) : launch_spmm_lanes<float, 1>(p, is_max, st);
     } else {
-        const bool vec = aligned16(p.X) && aligned16(p.out) && (p.ldx % 8 == 0) && (p.ldo % 4 == 0);
-        rc = vec ? launch_spmm_lanes<__nv_bfloat16, 8>(p, is_max, st)
-                 : launch_spmm_lanes<__nv_bfloat16, 1>(p, is_max, st);
+        const bool vec = aligned16(p.X) && (p.ldx % 8 == 0);
+        if (vec && stream_ok && p.F > 16 * 8) rc = launch_spmm_stream<__nv_bfloat16, 8>(p, p.nnz_hint, st);
+        else rc = vec ? launch_spmm_lanes<__nv_bfloat16, 8>(p, is_max, st)
+                      : launch_spmm_lanes<__nv_bfloat16, 1>(p, is_max, st);
     }
     if (rc != DGLLB_OK) return rc;
+finalize:
     if (use_plan && (p.addend || p.bias || p.epi)) {
         spmm_finalize_heavy_kernel<<<static_cast<unsigned>(plan->n_heavy_rows), 128, 0, st>>>(
             plan->heavy_rows, plan->n_heavy_rows, p.out, p.ldo, p.F, p.addend, p.ld_add, p.bias, p.epi);
@@ -442,8 +678,8 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
 
 extern "C" int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
                               const float* values, const void* X, int x_dtype, int64_t ldx,
-                              float* out, int64_t ldo, int64_t n_dst, int64_t n_src, int F,
-                              int reduce, const float* row_scale, const float* addend,
+                              float* out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t nnz,
+                              int F, int reduce, const float* row_scale, const float* addend,
                               int64_t ld_add, const float* bias, int epilogue,
                               int32_t* argmax_out, const dgllb_csr_plan* plan, void* stream) {
     DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && F >= 0, "spmm: negative size");
@@ -482,6 +718,7 @@ extern "C" int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32
     p.n_heavy_items = 0;
     p.chunk_edges = 0;
     p.row_cnt = nullptr;
+    p.nnz_hint = nnz;
     return spmm_run(p, x_dtype, reduce == DGLLB_MAX, plan, st);
 }
 

@@ -119,7 +119,7 @@ def spmm_csr(row_ptr, col_idx, x, values=None, reduce="sum", n_dst=None, out=Non
         argmax = torch.empty((n_dst, F), dtype=torch.int32, device=x.device)
     epi = (EPI_RELU if relu else 0) | (EPI_ELU if elu else 0)
     check(lib().dgllb_spmm_csr(_p(rp), is64, _p(col), _p(values), _p(x), xd, ldx, _p(out), ldo, n_dst,
-                               x.size(0), F, red, _p(row_scale), _p(addend), ld_add, _p(bias), epi,
+                               x.size(0), (col.numel() if col is not None else -1), F, red, _p(row_scale), _p(addend), ld_add, _p(bias), epi,
                                _p(argmax), plan._h if plan is not None else None, _stream()), "spmm_csr")
     return (out, argmax) if return_argmax else out
 

@@ -1,0 +1,344 @@
+"""Autograd-aware operators over the C-ABI kernels: the layer classes in ``dgll_b200.nn`` are built from these.
+
+Every forward AND backward runs on the hand-written kernels (``kernels.py`` -> ``libdgll_b200.so``); torch is used
+for memory, streams, elementwise glue on [n, F] tensors and autograd bookkeeping.  There is no CPU path: CPU tensors
+raise.
+
+  CsrGraph        static CSR by destination (+ lazily built transpose / nnz-split plan), converted once from the
+                  reference's adjacency formats (torch sparse COO as gcnconv.py:31 takes, dense 0/1 as gatconv.py:34
+                  / :115 take, edge_index as Evaluation/PPI/gcn_model.py:44-57 builds)
+  spmm            out = epi(reduce_e(values[e] * x[col[e]]) + bias)         (gcnconv.py:31, gcn_model.py:76, sageconv.py:32-38)
+  linear / mm     dense transform x @ W (+ b)                               (gcnconv.py:30, gatconv.py:117, sageconv.py:40,72)
+  gat_aggregate   fused SDDMM + edge softmax + aggregation                  (gatconv.py:30-54, 111-148)
+  gather_rows     feature row gather                                        (dgraph.py:105, storage.py:185-209)
+"""
+import torch
+
+from . import kernels as K
+
+_PRECISION = {"gemm": "fp32"}
+
+
+def set_gemm_precision(p):
+    """'fp32' = exact SIMT fp32 FMA (parity path, <=1e-5); 'bf16' = tcgen05 tensor cores, bf16 operands with fp32
+    accumulation in TMEM (<=1e-2)."""
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION["gemm"] = p
+
+
+def get_gemm_precision():
+    return _PRECISION["gemm"]
+
+
+# ------------------------------------------------------------------ graph ---
+class CsrGraph:
+    """CSR by destination row: ``row_ptr[n_dst+1]``, ``col[nnz]`` (source ids), optional ``values[nnz]``."""
+
+    HEAVY_ROW = 4096  # rows longer than this get an nnz-split plan
+
+    def __init__(self, row_ptr, col, values=None, n_src=None):
+        if not row_ptr.is_cuda:
+            raise RuntimeError("dgll_b200: CsrGraph needs CUDA tensors (there is no CPU fallback)")
+        self.row_ptr = row_ptr.contiguous()
+        self.col = None if col is None else (col if col.dtype == torch.int32 else col.to(torch.int32)).contiguous()
+        self.values = None if values is None else values.to(torch.float32).contiguous()
+        self.n_dst = self.row_ptr.numel() - 1
+        self.n_src = int(n_src) if n_src is not None else self.n_dst
+        self._t = None
+        self._perm = None
+        self._plan = False
+        self._deg = None
+        self._inv_deg = None
+
+    @property
+    def nnz(self):
+        return int(self.col.numel()) if self.col is not None else int(self.row_ptr[-1].item())
+
+    @property
+    def device(self):
+        return self.row_ptr.device
+
+    def degrees(self):
+        if self._deg is None:
+            self._deg = (self.row_ptr[1:] - self.row_ptr[:-1]).to(torch.float32)
+            self._inv_deg = torch.where(self._deg > 0, 1.0 / self._deg.clamp(min=1), torch.zeros_like(self._deg))
+        return self._deg
+
+    def inv_degrees(self):
+        self.degrees()
+        return self._inv_deg
+
+    def plan(self):
+        """nnz-split schedule when the graph has very long rows (Reddit-shaped skew); None otherwise."""
+        if self._plan is False:
+            self._plan = None
+            if self.n_dst > 0 and float(self.degrees().max().item()) > self.HEAVY_ROW:
+                self._plan = K.CsrPlan(self.row_ptr, chunk_edges=self.HEAVY_ROW)
+        return self._plan
+
+    def transpose(self):
+        """CsrGraph of A^T (values carried along); ``perm[e_T] = e`` kept for per-edge gradients."""
+        if self._t is None:
+            t_rp, t_col, t_val, perm = K.csr_transpose(self.row_ptr, self.col, self.n_src, values=self.values,
+                                                       want_perm=True)
+            self._t = CsrGraph(t_rp, t_col, t_val, n_src=self.n_dst)
+            self._perm = perm
+        return self._t
+
+    def with_values(self, values):
+        g = CsrGraph(self.row_ptr, self.col, values, n_src=self.n_src)
+        g._deg, g._inv_deg = self._deg, self._inv_deg
+        return g
+
+    # -- constructors from the reference's adjacency formats --
+    @staticmethod
+    def from_coo(rows, cols, n_dst, n_src=None, values=None):
+        """Stable COO -> CSR by row.  Duplicate (row, col) pairs are kept: they sum, as torch.sparse.mm does on an
+        uncoalesced COO (Evaluation/PPI/gcn_model.py:44-57 builds exactly that)."""
+        rows = rows.to(torch.int64)
+        order = torch.sort(rows, stable=True).indices
+        counts = torch.bincount(rows, minlength=n_dst)
+        row_ptr = torch.zeros(n_dst + 1, dtype=torch.int64, device=rows.device)
+        torch.cumsum(counts, 0, out=row_ptr[1:])
+        col = cols[order].to(torch.int32)
+        vals = None if values is None else values[order]
+        return CsrGraph(row_ptr, col, vals, n_src=n_src if n_src is not None else n_dst)
+
+    @staticmethod
+    def from_edge_index(edge_index, n, values=None):
+        """edge_index int64[2,E]; row index = edge_index[0] (gcn_model.py:56)."""
+        return CsrGraph.from_coo(edge_index[0], edge_index[1], n, n, values)
+
+    @staticmethod
+    def from_torch_sparse(adj):
+        if adj.layout == torch.sparse_csr:
+            return CsrGraph(adj.crow_indices(), adj.col_indices().to(torch.int32), adj.values(), n_src=adj.size(1))
+        idx = adj._indices() if not adj.is_coalesced() else adj.indices()
+        val = adj._values() if not adj.is_coalesced() else adj.values()
+        return CsrGraph.from_coo(idx[0], idx[1], adj.size(0), adj.size(1), val)
+
+    @staticmethod
+    def from_dense(adj):
+        """Edges = positions with adj > 0 in row-major order (gatconv.py:34 ``adj > 0``; :115 ``adj.nonzero()``)."""
+        nz = (adj > 0).nonzero()
+        return CsrGraph.from_coo(nz[:, 0], nz[:, 1], adj.size(0), adj.size(1), None)
+
+
+class _Key:
+    """holder attached to the adjacency tensor so a converted graph lives exactly as long as that tensor object."""
+    __slots__ = ("graph", "version")
+
+
+def as_csr(adj, binary=False):
+    """Accepts CsrGraph | torch sparse COO/CSR | dense [n, m] | (row_ptr, col[, values]).  Conversions of tensor
+    inputs are cached per tensor object (the reference passes the same ``adj`` every step)."""
+    if isinstance(adj, CsrGraph):
+        return adj
+    if isinstance(adj, (tuple, list)):
+        return CsrGraph(*adj)
+    if not isinstance(adj, torch.Tensor):
+        raise TypeError("unsupported adjacency type %r" % type(adj))
+    if not adj.is_cuda:
+        raise RuntimeError("dgll_b200: adjacency must live on a CUDA device (there is no CPU fallback)")
+    holder = getattr(adj, "_dgllb_csr", None)
+    ver = adj._version if adj.layout == torch.strided else 0
+    if holder is not None and holder.version == (ver, binary):
+        return holder.graph
+    if adj.layout == torch.strided:
+        g = CsrGraph.from_dense(adj)
+        if not binary:
+            nz = (adj > 0).nonzero()
+            g = g.with_values(adj[nz[:, 0], nz[:, 1]])
+    else:
+        g = CsrGraph.from_torch_sparse(adj)
+        if binary:
+            g = g.with_values(None)
+    holder = _Key()
+    holder.graph, holder.version = g, (ver, binary)
+    try:
+        adj._dgllb_csr = holder
+    except Exception:
+        pass
+    return g
+
+
+# ------------------------------------------------------------------- SpMM ---
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, values, bias, graph, reduce, relu, F):
+        g = graph if values is None else graph.with_values(values)
+        want_argmax = reduce == "max" and (x.requires_grad or (values is not None and values.requires_grad))
+        plan = graph.plan() if reduce != "max" else None
+        res = K.spmm_csr(g.row_ptr, g.col, x, values=g.values, reduce=reduce, n_dst=g.n_dst, bias=bias, relu=relu,
+                         return_argmax=want_argmax, plan=plan, F=F)
+        out, argmax = res if want_argmax else (res, None)
+        ctx.graph, ctx.reduce, ctx.relu = graph, reduce, relu
+        ctx.has_values, ctx.has_bias = values is not None, bias is not None
+        ctx.save_for_backward(x, values, out if relu else None, argmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, values, out, argmax = ctx.saved_tensors
+        graph = ctx.graph
+        g = grad.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        gx = gv = gb = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        if ctx.reduce == "max":
+            if ctx.needs_input_grad[0]:
+                if ctx.has_values:
+                    raise NotImplementedError("max aggregation with learnable edge values")
+                gx = K.spmm_max_backward(graph.col, argmax, g, x.size(0))
+                if gx.size(1) != x.size(1):
+                    gx = torch.nn.functional.pad(gx, (0, x.size(1) - gx.size(1)))
+            return gx, None, gb, None, None, None, None
+        if ctx.reduce == "mean":
+            g = g * graph.inv_degrees()[:, None]
+        if ctx.needs_input_grad[0]:
+            gt = graph.transpose()
+            tvals = None
+            if ctx.has_values:
+                tvals = values.detach()[graph._perm.long()]
+            elif gt.values is not None:
+                tvals = gt.values
+            gx = K.spmm_csr(gt.row_ptr, gt.col, g, values=tvals, reduce="sum", n_dst=gt.n_dst,
+                            plan=gt.plan())
+            if gx.size(1) != x.size(1):
+                gx = torch.nn.functional.pad(gx, (0, x.size(1) - gx.size(1)))
+            if gx.dtype != x.dtype:
+                gx = gx.to(x.dtype)
+        if ctx.has_values and ctx.needs_input_grad[1]:
+            # d values[e] = <g[row(e)], x[col[e]]>  — the SDDMM SpecialSpmmFunction.backward computes densely (gatconv.py:76-78)
+            gv = K.sddmm_csr(graph.row_ptr, graph.col, g, x[:, :g.size(1)].float())
+        return gx, gv, gb, None, None, None, None
+
+
+def spmm(adj, x, values=None, reduce="sum", bias=None, relu=False, F=None):
+    """Neighbourhood aggregation with autograd.  ``values`` overrides the graph's edge values (and may require grad)."""
+    graph = as_csr(adj)
+    if values is None and graph.values is not None:
+        values_arg = None  # static values ride inside the graph object
+    else:
+        values_arg = values
+    return _SpmmFn.apply(x, values_arg, bias, graph, reduce, relu, F)
+
+
+# ----------------------------------------------------------------- linear ---
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, relu, precision):
+        out = K.gemm(x, w, bias=bias, relu=relu, precision=precision)
+        ctx.relu, ctx.precision = relu, precision
+        ctx.save_for_backward(x, w, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w, out = ctx.saved_tensors
+        g = grad.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = K.gemm(g, w, trans_b=True, precision=ctx.precision)      # dX = G W^T
+        if ctx.needs_input_grad[1]:
+            gw = K.gemm(x, g, trans_a=True, precision=ctx.precision)      # dW = X^T G
+        if ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb, None, None
+
+
+def linear(x, w, bias=None, relu=False, precision=None):
+    """x[M,K] @ w[K,N] (+ bias)(relu) on the device GEMM (fp32 exact or tcgen05 bf16)."""
+    lead = None
+    if x.dim() > 2:
+        lead = x.shape[:-1]
+        x = x.reshape(-1, x.size(-1))
+    out = _LinearFn.apply(x, w, bias, relu, precision or _PRECISION["gemm"])
+    return out if lead is None else out.reshape(*lead, out.size(-1))
+
+
+def mm(a, b):
+    return linear(a, b)
+
+
+# -------------------------------------------------------------------- GAT ---
+class _GatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wh, el, er, graph, heads, slope, mode):
+        out, rmax, rsum = K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode,
+                                        save_stats=True, n_dst=graph.n_dst)
+        ctx.graph, ctx.heads, ctx.slope, ctx.mode = graph, heads, slope, mode
+        ctx.save_for_backward(wh, el, er, out, rmax, rsum)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        wh, el, er, out, rmax, rsum = ctx.saved_tensors
+        graph = ctx.graph
+        gt = graph.transpose()
+        d_wh, d_el, d_er = K.gat_backward(graph.row_ptr, graph.col, gt.row_ptr, gt.col, graph._perm, wh, el, er, out,
+                                          rmax, rsum, grad.contiguous(), ctx.heads, ctx.slope, mode=ctx.mode)
+        return d_wh, d_el, d_er, None, None, None, None
+
+
+def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False):
+    """Fused SDDMM + edge-softmax + aggregation.  ``wh`` [n_src, heads*D]; ``el`` [n_dst, heads]; ``er`` [n_src, heads]."""
+    graph = as_csr(adj, binary=True)
+    if torch.is_grad_enabled() and (wh.requires_grad or el.requires_grad or er.requires_grad):
+        out = _GatFn.apply(wh, el, er, graph, heads, slope, mode)
+        return torch.nn.functional.elu(out) if elu else out
+    return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst)
+
+
+# ----------------------------------------------------------------- gather ---
+class _GatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, ids):
+        ctx.n = table.size(0)
+        ctx.save_for_backward(ids)
+        return K.gather_rows(table, ids)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ids,) = ctx.saved_tensors
+        # scatter-add of gradient rows = aggregation over the transposed "gather graph": rows sorted by id
+        order = torch.sort(ids.to(torch.int64), stable=True).indices
+        counts = torch.bincount(ids.to(torch.int64), minlength=ctx.n)
+        rp = torch.zeros(ctx.n + 1, dtype=torch.int64, device=ids.device)
+        torch.cumsum(counts, 0, out=rp[1:])
+        g2 = grad.reshape(grad.size(0), -1).contiguous()
+        out = K.spmm_csr(rp, order.to(torch.int32), g2, reduce="sum", n_dst=ctx.n)
+        return out.reshape((ctx.n,) + tuple(grad.shape[1:])), None
+
+
+def gather_rows(table, ids):
+    """``table[ids]`` through the TMA row-gather kernel (bit-exact copy); differentiable w.r.t. ``table``."""
+    if table.requires_grad and torch.is_grad_enabled():
+        return _GatherFn.apply(table, ids)
+    return K.gather_rows(table, ids)
+
+
+# ---------------------------------------------------------------- pooling ---
+def segment_reduce(x, batch, size=None, reduce="sum"):
+    """scatter(x, batch, dim=0, reduce=...) for a SORTED batch vector = segment reduce (Pooling.py:37,59,81).
+    An unsorted ``batch`` is sorted first (stable), which keeps the result identical to scatter()."""
+    if batch is None:
+        rp = torch.tensor([0, x.size(0)], dtype=torch.int64, device=x.device)
+        col = torch.arange(x.size(0), device=x.device, dtype=torch.int32)
+        return spmm(CsrGraph(rp, col, n_src=x.size(0)), x, reduce=reduce)
+    batch = batch.to(torch.int64)
+    size = int(batch.max().item() + 1) if size is None else int(size)
+    if batch.numel() > 1 and bool((batch[1:] < batch[:-1]).any().item()):
+        order = torch.sort(batch, stable=True).indices
+        x = gather_rows(x, order)
+        batch = batch[order]
+    counts = torch.bincount(batch, minlength=size)
+    rp = torch.zeros(size + 1, dtype=torch.int64, device=x.device)
+    torch.cumsum(counts, 0, out=rp[1:])
+    g = CsrGraph(rp, torch.arange(x.size(0), device=x.device, dtype=torch.int32), n_src=x.size(0))
+    return spmm(g, x, reduce=reduce)

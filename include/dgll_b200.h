@@ -95,6 +95,9 @@ void dgllb_csr_plan_destroy(dgllb_csr_plan* plan);
  * (pass col_idx == NULL: identity columns, i.e. a segment reduce).
  *
  *   row_ptr     int32[n_dst+1] or int64[n_dst+1] (row_ptr_is64)
+ *   nnz         an UPPER BOUND on row_ptr[n_dst] known to the host (normally the length of col_idx); it
+ *               sizes the grid of the streaming (row-aligned nnz-split) kernel without a device read-back.
+ *               Pass a negative value when unknown: the one-warp-per-row kernel runs instead.
  *   col_idx     int32[nnz] (rows of X; NULL = identity: column e is row e)
  *   values      float[nnz] or NULL (all ones)
  *   X           x_dtype[n_src, ldx] row-major (DGLLB_F32 / DGLLB_BF16), F <= ldx
@@ -105,14 +108,14 @@ void dgllb_csr_plan_destroy(dgllb_csr_plan* plan);
  *   bias        float[F] or NULL; epilogue = bit-or of DGLLB_EPI_*
  *   argmax_out  int32[n_dst, F] or NULL (DGLLB_MAX only): edge index e that won,
  *               -1 for empty rows (needed by the max backward)
- * 128-bit vector loads are used when X/out/addend are 16-byte aligned and the
- * leading dimensions are multiples of 4 (f32) / 8 (bf16); otherwise a scalar
- * path runs.  accumulation is fp32 in CSR edge order per row (deterministic
- * unless `plan` splits the row).
+ * 128-bit vector loads are used when X is 16-byte aligned and ldx is a multiple
+ * of 4 (f32) / 8 (bf16); 128-bit stores when out is 16-byte aligned and ldo a multiple
+ * of 4; otherwise scalar accesses.  Accumulation is fp32 in CSR edge order per row
+ * (deterministic unless `plan` splits the row).
  */
 int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
                    const float* values, const void* X, int x_dtype, int64_t ldx,
-                   float* out, int64_t ldo, int64_t n_dst, int64_t n_src, int F,
+                   float* out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t nnz, int F,
                    int reduce, const float* row_scale, const float* addend,
                    int64_t ld_add, const float* bias, int epilogue,
                    int32_t* argmax_out, const dgllb_csr_plan* plan, void* stream);

@@ -517,3 +517,57 @@ def test_ppi_golden_layer_on_device(K):
     support = K.gemm(dev(g["feats"].astype(np.float32)), dev(g["w0"].astype(np.float32)))
     h1 = K.spmm_csr(dev(rp), dev(col), support, reduce="sum", relu=True)
     assert rel_err(h1.cpu().numpy(), g["h1"]) <= FP32_TOL
+
+
+# ------------------------------------------------ SpMM kernel families -----
+@pytest.mark.parametrize("family", ["rowsplit", "stream", "bulk"])
+@pytest.mark.parametrize("F,ld,dt", [(602, 604, "f32"), (256, 256, "f32"), (128, 128, "f32"), (100, 100, "f32"),
+                                     (602, 608, "bf16"), (1000, 1000, "f32"), (36, 36, "f32")])
+def test_spmm_kernel_families_agree_with_oracle(K, family, F, ld, dt, monkeypatch):
+    """DGLLB_SPMM_KERNEL pins the one-warp-per-row, the rolling-LDG streaming or the TMA-staged kernel: all three
+    must match the oracle on ragged blocks (empty rows, short rows, one long row, rows straddling chunk borders)."""
+    monkeypatch.setenv("DGLLB_SPMM_KERNEL", family)
+    rng = np.random.default_rng(F + len(family))
+    n_dst, n_src = 2500, 4000
+    rp, col = rand_csr(rng, n_dst, n_src, 37, heavy=[(5, 1500), (2499, 300)], empty_frac=0.15)
+    rp[-3:] = rp[-3]  # trailing empty rows
+    col = col[:rp[-1]]
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    vals = rng.random(col.size).astype(np.float32) + 0.1
+    bias = rng.standard_normal(F).astype(np.float32)
+    add = rng.standard_normal((n_dst, F)).astype(np.float32)
+    rs = rng.random(n_dst).astype(np.float32)
+    tx = padded(x, ld)
+    tol = FP32_TOL
+    if dt == "bf16":
+        tx = tx.to(torch.bfloat16)
+        x = tx[:, :F].float().cpu().numpy()
+    for rpt in (np.int64, np.int32):
+        for red in ("sum", "mean"):
+            ref = oracle.spmm_csr(rp, col, x, reduce=red)
+            out = K.spmm_csr(dev(rp.astype(rpt)), dev(col), tx, reduce=red, F=F)
+            assert rel_err(out.cpu().numpy(), ref) <= tol, (family, red)
+    ref = oracle.spmm_csr(rp, col, x, values=vals, reduce="mean", row_scale=rs, addend=add, bias=bias, relu=True)
+    out = K.spmm_csr(dev(rp), dev(col), tx, values=dev(vals), reduce="mean", row_scale=dev(rs), addend=dev(add),
+                     bias=dev(bias), relu=True, F=F)
+    assert rel_err(out.cpu().numpy(), ref) <= tol
+    # all rows empty / no edges at all
+    rp0 = np.zeros(n_dst + 1, dtype=np.int64)
+    out = K.spmm_csr(dev(rp0), torch.zeros(0, dtype=torch.int32, device="cuda"), tx, reduce="mean", bias=dev(bias), F=F)
+    assert rel_err(out.cpu().numpy(), np.broadcast_to(bias, (n_dst, F))) <= tol
+
+
+@pytest.mark.parametrize("family", ["rowsplit", "stream", "bulk"])
+def test_spmm_families_deterministic(K, family, monkeypatch):
+    monkeypatch.setenv("DGLLB_SPMM_KERNEL", family)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n, F = 20000, 602
+    deg = torch.randint(0, 40, (n,), device="cuda", generator=g)
+    rp = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    rp[1:] = torch.cumsum(deg, 0)
+    col = torch.randint(0, n, (int(rp[-1].item()),), device="cuda", generator=g, dtype=torch.int32)
+    x = torch.zeros(n, 604, device="cuda")
+    x[:, :F] = torch.randn(n, F, device="cuda", generator=g)
+    a = K.spmm_csr(rp, col, x, reduce="mean", F=F)
+    b = K.spmm_csr(rp, col, x, reduce="mean", F=F)
+    assert torch.equal(a, b)

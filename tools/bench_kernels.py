@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""Per-kernel throughput on the BASELINE.json shapes (not the driver's bench line — see bench.py).
+
+Prints one JSON object per measurement: kernel, shape, ms, algorithmic GB/s (SURVEY.md §8 d formulas) and the
+fraction of the measured HBM peak.  Inputs are larger than L2 or rotated between iterations.
+
+  python tools/bench_kernels.py [--which full,gather,bin,gat,block] [--iters 10]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from dgll_b200 import graphs as G  # noqa: E402
+from dgll_b200 import kernels as K  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def report(name, shape, ms, nbytes, extra=None):
+    d = {"kernel": name, "shape": shape, "ms": round(ms, 4), "alg_GB": round(nbytes / 1e9, 3),
+         "GBps": round(nbytes / ms / 1e6, 1), "frac_of_measured_hbm": round(nbytes / ms / 1e6 / peak(), 3)}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="full,gather,bin,gat,block")
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    which = set(args.which.split(","))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    N, NNZ, F, _ = G.SHAPES["reddit"]
+
+    if which & {"full", "bin", "block", "gather"}:
+        rp, col = G.rmat_csr(N, NNZ, seed=0, device=dev)
+        deg = rp[1:] - rp[:-1]
+        print(json.dumps({"graph": "reddit-shaped rmat", "N": N, "nnz": int(rp[-1]), "max_deg": int(deg.max()),
+                          "rows_gt_4096": int((deg > 4096).sum()), "edges_in_rows_gt_4096": int(deg[deg > 4096].sum())}),
+              flush=True)
+
+    if "full" in which:
+        for Fw, dt in ((602, torch.float32), (256, torch.float32), (602, torch.bfloat16), (256, torch.bfloat16)):
+            x = G.feature_table(N, Fw, seed=1, device=dev, dtype=dt)
+            b = x.element_size()
+            out = torch.empty((N, (Fw + 3) // 4 * 4), device=dev)[:, :Fw]
+            nbytes = NNZ * (4 + Fw * b) + N * (Fw * 4 + 8)
+            plan = K.CsrPlan(rp, chunk_edges=4096)
+            for fam in ("rowsplit", "stream", "bulk"):
+                os.environ["DGLLB_SPMM_KERNEL"] = fam
+                ms = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=Fw), args.iters)
+                report("spmm_full_graph[%s]" % fam, "F=%d %s" % (Fw, str(dt).split(".")[-1]), ms, nbytes)
+            os.environ["DGLLB_SPMM_KERNEL"] = "rowsplit"
+            ms = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=Fw, plan=plan), args.iters)
+            report("spmm_full_graph[rowsplit+plan]", "F=%d %s" % (Fw, str(dt).split(".")[-1]), ms, nbytes,
+                   {"heavy_rows": plan.n_heavy_rows, "chunks": plan.n_chunks})
+            os.environ.pop("DGLLB_SPMM_KERNEL", None)
+            del x, out
+
+    if "gather" in which:
+        table = G.feature_table(N, F, seed=1, device=dev)
+        g = torch.Generator(device=dev).manual_seed(3)
+        for M in (160000, 1000000):
+            ids = torch.randint(0, N, (M,), device=dev, generator=g)
+            out = torch.empty((M, table.size(1)), device=dev)
+            ms = timeit(lambda: K.gather_rows(table, ids, out=out), args.iters)
+            report("gather_rows[tma]", "M=%d row=%dB" % (M, table.size(1) * 4), ms, M * (8 + 2 * table.size(1) * 4))
+            ms = timeit(lambda: torch.index_select(table, 0, ids, out=out), args.iters)
+            report("torch.index_select (library comparator)", "M=%d" % M, ms, M * (8 + 2 * table.size(1) * 4))
+        del table
+
+    if "bin" in which:
+        x = G.feature_table(N, F, seed=1, device=dev)
+        packed = K.binarize_pack(x[:, :F])
+        wpr = packed.size(1)
+        nbytes = NNZ * (4 + 4 * wpr) + N * (4 * F + 8)
+        ms = timeit(lambda: K.bin_spmm_csr(rp, col, packed, F, mode="mean"), args.iters)
+        report("bin_spmm_csr", "F=%d words/row=%d" % (F, wpr), ms, nbytes)
+        ms_pack = timeit(lambda: K.binarize_pack(x[:, :F]), args.iters)
+        report("binarize_pack", "N=%d F=%d" % (N, F), ms_pack, N * (F * 4 + wpr * 4))
+        out = torch.empty((N, 604), device=dev)[:, :F]
+        ms32 = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=F), args.iters)
+        report("spmm_full_graph fp32 (C4 comparator)", "F=%d" % F, ms32, NNZ * (4 + F * 4) + N * (F * 4 + 8),
+               {"speedup_binarized_vs_fp32": round(ms32 / ms, 2)})
+        del x, packed, out
+
+    if "block" in which:
+        table = G.feature_table(N, F, seed=1, device=dev)
+        gen = torch.Generator(device=dev).manual_seed(5)
+        for batch in (1024, 8192):
+            seeds = torch.randperm(int(0.66 * N), device=dev, generator=gen)[:batch]
+            b0, b1 = G.sample_blocks(rp, col, seeds, (25, 10), rng_seed=9)
+            out = torch.empty((b0.num_dst, 604), device=dev)[:, :F]
+            nbytes = b0.num_edges() * (4 + F * 4) + b0.num_dst * (F * 4 + 4)
+            for fam in ("rowsplit", "stream", "bulk"):
+                os.environ["DGLLB_SPMM_KERNEL"] = fam
+                ms = timeit(lambda: K.spmm_csr(b0.row_ptr, b0.col_global, table, reduce="mean", out=out, F=F), 30)
+                report("spmm_block0[%s]" % fam, "batch=%d n_dst=%d nnz=%d" % (batch, b0.num_dst, b0.num_edges()), ms, nbytes)
+            os.environ.pop("DGLLB_SPMM_KERNEL", None)
+        del table
+
+    if "gat" in which:
+        Np, E, Fp, _ = G.SHAPES["products"]
+        rp, col = G.rmat_csr(Np, 2 * E, seed=2, device=dev, symmetric=True)
+        heads, D = 4, 64
+        g = torch.Generator(device=dev).manual_seed(4)
+        wh = torch.randn((Np, heads * D), device=dev, generator=g)
+        el = torch.randn((Np, heads), device=dev, generator=g)
+        er = torch.randn((Np, heads), device=dev, generator=g)
+        out = torch.empty_like(wh)
+        nnz = col.numel()
+        nbytes = nnz * (4 + heads * D * 4 + heads * 4) + Np * (heads * D * 4 + heads * 4 + 8)
+        ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out), args.iters)
+        report("gat_forward (fused SDDMM+softmax+SpMM)", "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes)
+        ms = timeit(lambda: K.spmm_csr(rp, col, wh, reduce="sum", out=out), args.iters)
+        report("spmm_full_graph (same graph, F=256)", "products-shaped", ms, nnz * (4 + 256 * 4) + Np * (256 * 4 + 8))
+
+
+if __name__ == "__main__":
+    main()
