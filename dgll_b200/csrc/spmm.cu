@@ -643,11 +643,14 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
     p.out_vec = aligned16(p.out) && (p.ldo % 4 == 0);
     // streaming kernel: sum/mean over an explicit col_idx with a host-known nnz bound, wide rows, no split plan
     bool stream_ok = !is_max && !use_plan && p.col && !p.row_cnt && p.nnz_hint >= 0;
-    // DGLLB_SPMM_KERNEL=rowsplit|stream|bulk pins one kernel family (profiling / A-B runs); default = best available
+    // Kernel choice (measured on B200, profiles/r01_kernels*.jsonl): one-warp-per-row wins on small sampled
+    // blocks, the rolling-LDG streaming kernel on large ones (>= 2^19 edges), row-split + nnz-split plan on
+    // skewed full graphs; the TMA-staged kernel is correct but slower than both LDG kernels on this part and
+    // only runs when pinned.  DGLLB_SPMM_KERNEL=rowsplit|stream|bulk pins one family (profiling / A-B runs).
     const char* force = getenv("DGLLB_SPMM_KERNEL");
-    const bool want_bulk = !force || force[0] == 'b';
     if (force && force[0] == 'r') stream_ok = false;
-    if (stream_ok && want_bulk) {
+    if (!force && p.nnz_hint < (1ll << 19)) stream_ok = false;
+    if (stream_ok && force && force[0] == 'b') {
         rc = spmm_bulk_try(p, x_dtype, p.nnz_hint, st);
         if (rc != DGLLB_ERR_UNSUPPORTED) {
             if (rc != DGLLB_OK) return rc;
