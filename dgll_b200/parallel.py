@@ -1,0 +1,121 @@
+"""One-box multi-GPU plumbing for the aggregation path: node-range partition, halo feature exchange, fused gradient
+all-reduce.  One process per GPU, ``torch.distributed`` (NCCL over NVLink on the box, gloo in the CPU tests).
+
+The reference has no partitioned training (SURVEY.md §8 e): its multi-GPU scheme is data parallelism with a
+per-parameter ``all_reduce`` (GPU Accelerator/MQGCN.py:55-67).  ``allreduce_gradients`` keeps that semantics in ONE
+collective; ``HaloExchange`` is the new piece for graphs whose feature table is sharded by node range
+(papers100M-shaped, BASELINE.json configs[4]).
+
+Host logic only lives here.  Row gathers go through ``gather_fn`` — by default the TMA gather kernel
+(``kernels.gather_rows``, CUDA only, no fallback); the gloo tests inject a CPU gather to exercise the exchange logic.
+"""
+import torch
+import torch.distributed as dist
+
+
+def part_size(n_nodes, world):
+    return (n_nodes + world - 1) // world
+
+
+def owner_of(ids, n_nodes, world):
+    """Node-range partition: node u belongs to rank ``u // ceil(N/P)`` — no lookup table."""
+    return torch.div(ids, part_size(n_nodes, world), rounding_mode="floor")
+
+
+def local_range(rank, n_nodes, world):
+    p = part_size(n_nodes, world)
+    return min(rank * p, n_nodes), min((rank + 1) * p, n_nodes)
+
+
+def _default_gather(table, ids):
+    from . import kernels as K  # CUDA only; raises on CPU tensors
+    return K.gather_rows(table, ids)
+
+
+class HaloExchange:
+    """Fetch feature rows of arbitrary GLOBAL node ids from a table sharded by node range.
+
+    fetch(ids):  1. bucket ids by owner (stable)                 2. all_to_all_single(counts)
+                 3. all_to_all_single(local row offsets)         4. owners gather rows (TMA gather kernel) into the
+                 send buffer                                     5. all_to_all_single(rows)   6. undo the bucketing
+    Rows owned by the caller never leave the device (they are gathered locally in step 4 like any other bucket, the
+    self-bucket of all_to_all_single is a device copy).  ``stats`` counts local/remote rows for the scaling report.
+    """
+
+    def __init__(self, n_nodes, local_table, group=None, gather_fn=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_nodes = n_nodes
+        self.table = local_table
+        self.part = part_size(n_nodes, self.world)
+        lo, hi = local_range(self.rank, n_nodes, self.world)
+        if local_table.size(0) != hi - lo:
+            raise ValueError("rank %d must hold rows [%d, %d) of the table, got %d rows" %
+                             (self.rank, lo, hi, local_table.size(0)))
+        self.gather_fn = gather_fn or _default_gather
+        self.stats = {"rows": 0, "remote_rows": 0, "calls": 0}
+
+    def plan(self, ids):
+        """Bucketing + the two small exchanges.  Returns a dict reused by ``exchange`` (lets the caller overlap the id
+        exchange of batch k+1 with the aggregation of batch k)."""
+        ids = ids.to(torch.int64)
+        owner = owner_of(ids, self.n_nodes, self.world)
+        order = torch.sort(owner, stable=True).indices
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        if self.world > 1:
+            dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        else:
+            recv_counts.copy_(send_counts)
+        send_split = send_counts.tolist()
+        recv_split = recv_counts.tolist()
+        local_off = (ids - owner * self.part)[order].contiguous()
+        req = torch.empty(sum(recv_split), dtype=torch.int64, device=ids.device)
+        if self.world > 1:
+            dist.all_to_all_single(req, local_off, recv_split, send_split, group=self.group)
+        else:
+            req.copy_(local_off)
+        self.stats["rows"] += ids.numel()
+        self.stats["remote_rows"] += ids.numel() - send_split[self.rank]
+        self.stats["calls"] += 1
+        return {"order": order, "send_split": send_split, "recv_split": recv_split, "req": req, "n": ids.numel()}
+
+    def exchange(self, plan):
+        rows_out = self.gather_fn(self.table, plan["req"])            # rows other ranks (and we) asked for
+        width = rows_out.shape[1:]
+        recv = torch.empty((plan["n"],) + tuple(width), dtype=rows_out.dtype, device=rows_out.device)
+        if self.world > 1:
+            dist.all_to_all_single(recv, rows_out.contiguous(), plan["send_split"], plan["recv_split"],
+                                   group=self.group)
+        else:
+            recv.copy_(rows_out)
+        out = torch.empty_like(recv)
+        out[plan["order"]] = recv
+        return out
+
+    def fetch(self, ids):
+        return self.exchange(self.plan(ids))
+
+
+def allreduce_gradients(params, group=None, average=True):
+    """Sum (and average) every ``.grad`` in ONE flat-buffer all-reduce (replaces the per-parameter loop of
+    GPU Accelerator/MQGCN.py:55-67 — 4-6 latency-bound NCCL calls per step — and DDP buckets, :141-144)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def shard_seeds(seeds, n_nodes, rank, world):
+    """Seeds owned by ``rank`` under the node-range partition (batches are local by destination)."""
+    lo, hi = local_range(rank, n_nodes, world)
+    return seeds[(seeds >= lo) & (seeds < hi)]
