@@ -571,3 +571,52 @@ def test_spmm_families_deterministic(K, family, monkeypatch):
     a = K.spmm_csr(rp, col, x, reduce="mean", F=F)
     b = K.spmm_csr(rp, col, x, reduce="mean", F=F)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------- tcgen05 GEMM ------
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 64), (300, 64, 50), (1000, 256, 602), (17, 5, 3), (4096, 41, 256),
+                                    (129, 130, 65), (2000, 256, 1204)])
+def test_gemm_tcgen05_bf16_parity(K, M, N, K_):
+    """precision='bf16': tcgen05.mma with bf16 operands, fp32 accumulation in TMEM.  Bar: 1e-2 of max|ref| against the
+    fp64 product of the ORIGINAL fp32 operands, and 1e-5 against the product of the bf16-rounded operands."""
+    rng = np.random.default_rng(M + N)
+    a = rng.standard_normal((M, K_)).astype(np.float32)
+    b = rng.standard_normal((K_, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out = K.gemm(dev(a), dev(b), precision="bf16").cpu().numpy()
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    assert rel_err(out, ref) <= BF16_TOL
+    ar = dev(a).to(torch.bfloat16).float().cpu().numpy().astype(np.float64)
+    br = dev(b).to(torch.bfloat16).float().cpu().numpy().astype(np.float64)
+    assert rel_err(out, ar @ br) <= 2e-5
+    # epilogue: bias + relu; transposed operands; accumulate
+    out = K.gemm(dev(a), dev(b), bias=dev(bias), relu=True, precision="bf16").cpu().numpy()
+    assert rel_err(out, np.maximum(ar @ br + bias, 0)) <= 2e-5
+    g = rng.standard_normal((M, N)).astype(np.float32)
+    gr = dev(g).to(torch.bfloat16).float().cpu().numpy().astype(np.float64)
+    acc = rng.standard_normal((K_, N)).astype(np.float32)
+    o = dev(acc)
+    K.gemm(dev(a), dev(g), trans_a=True, out=o, accumulate=True, precision="bf16")      # dW += A^T G
+    assert rel_err(o.cpu().numpy(), acc + ar.T @ gr) <= 2e-5
+    o2 = K.gemm(dev(g), dev(b), trans_b=True, precision="bf16").cpu().numpy()            # dX = G W^T
+    assert rel_err(o2, gr @ br.T) <= 2e-5
+
+
+def test_layers_run_on_tensor_core_path(K):
+    """ops.set_gemm_precision('bf16') routes every dense transform of a layer through tcgen05; GCN output stays within
+    the bf16 bar of the fp32 path."""
+    import dgll_b200.nn as nn
+    from dgll_b200 import ops
+    from conftest import golden
+    g = golden("nn_gcn")
+    n = g["x"].shape[0]
+    adj = torch.sparse_coo_tensor(dev(g["adj_indices"]).long(), dev(g["adj_values"]).float(), (n, n))
+    model = nn.GCN(32, 16, 7, dropout=0.0).cuda().eval()
+    x = dev(g["x"]).float()
+    ref = model(x, adj)
+    ops.set_gemm_precision("bf16")
+    try:
+        out = model(x, adj)
+    finally:
+        ops.set_gemm_precision("fp32")
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= BF16_TOL
