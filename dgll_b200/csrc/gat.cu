@@ -91,16 +91,35 @@ gat_forward_kernel(const GatParams p) {
 #pragma unroll
     for (int a = 0; a < VE; ++a) acc[a] = 0.f;
 
+    // software pipeline over the row's LANES-edge chunks: column ids are fetched two chunks ahead and the source
+    // attention scalars er[col] one chunk ahead, so the dependent chain col -> er -> exp -> row loads of the next
+    // chunk overlaps the feature-row loads of the current one (profiles/r01_gat_forward.txt: latency bound).
+    const float* __restrict__ erh = p.er + head;
+    int c_cur = 0, c_nxt = 0;
+    float er_cur = 0.f;
+    if (beg + lig < end) {
+        c_cur = __ldg(p.col + beg + lig);
+        er_cur = __ldg(erh + static_cast<long long>(c_cur) * p.ld_e);
+    }
+    if (beg + LANES + lig < end) c_nxt = __ldg(p.col + beg + LANES + lig);
+
     for (long long e0 = beg; e0 < end; e0 += LANES) {
         const int n = static_cast<int>(min(static_cast<long long>(LANES), end - e0));
-        int my_c = 0;
+        // prefetch: er of the next chunk (its ids arrived during the previous iteration), ids of the one after
+        float er_nxt = 0.f;
+        if (e0 + LANES + lig < end) er_nxt = __ldg(erh + static_cast<long long>(c_nxt) * p.ld_e);
+        int c_nxt2 = 0;
+        if (e0 + 2 * LANES + lig < end) c_nxt2 = __ldg(p.col + e0 + 2 * LANES + lig);
+        const int my_c = c_cur;
         float my_s = -INFINITY;
         if (lig < n) {
-            my_c = __ldg(p.col + e0 + lig);
-            float z = el_i + __ldg(p.er + static_cast<long long>(my_c) * p.ld_e + head);
+            float z = el_i + er_cur;
             z = z > 0.f ? z : p.slope * z;
             my_s = p.sign * z;
         }
+        c_cur = c_nxt;
+        er_cur = er_nxt;
+        c_nxt = c_nxt2;
         const float mc = group_max<LANES>(my_s, gmask);
         const float m_new = fmaxf(m, mc);
         const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);

@@ -16,8 +16,9 @@
 namespace dgllb {
 
 constexpr int kGatherWarps = 8;      // warps per CTA
-constexpr int kSlots = 4;            // ring depth per warp
+constexpr int kMaxSlots = 16;        // ring depth per warp (upper bound)
 constexpr int kSlotBytes = 4096;     // piece size (rows longer than this are split)
+constexpr int kGatherSmem = 200 * 1024;
 
 struct GatherSrc {
     // resolves the source address of output row i
@@ -46,59 +47,87 @@ __device__ __forceinline__ const char* resolve_row(const GatherSrc& s, long long
     return s.table + id * s.stride;
 }
 
-// TMA bulk-copy gather.  grid = persistent CTAs, each warp strides over pieces.
+// TMA bulk-copy gather.  grid = persistent CTAs; every warp owns a CONTIGUOUS range of (row, piece) items so
+// its ids are read coalesced, 32 at a time, by all lanes (the first version let the single issuing lane load
+// each id itself and stalled ~1 us per row on that dependent load — profiles/r01_bin_gather.txt).  The lanes
+// park (src, dst, bytes) of the next 64 items in shared memory; lane 0 runs the copy pipeline: a ring of
+// `slots` shared-memory slots, loads `slots` items ahead of the stores.
 __global__ void __launch_bounds__(kGatherWarps * 32)
 gather_bulk_kernel(const GatherSrc src, char* __restrict__ out, long long out_stride, long long n_rows,
-                   long long row_bytes, int pieces_per_row) {
+                   long long row_bytes, int pieces_per_row, int slots, int slot_bytes, int piece_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[kGatherWarps][kSlots];
+    __shared__ uint64_t bars[kGatherWarps][kMaxSlots];
+    __shared__ unsigned long long m_src[kGatherWarps][64], m_dst[kGatherWarps][64];
+    __shared__ uint32_t m_bytes[kGatherWarps][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;  // one elected lane per warp drives the copies
-    unsigned char* ring = smem + static_cast<size_t>(warp) * kSlots * kSlotBytes;
-    for (int s = 0; s < kSlots; ++s) mbar_init(&bars[warp][s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned char* ring = smem + static_cast<size_t>(warp) * slots * slot_bytes;
+    if (lane == 0) {
+        for (int s = 0; s < slots; ++s) mbar_init(&bars[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     const long long n_items = n_rows * pieces_per_row;
+    const long long n_warps = static_cast<long long>(gridDim.x) * kGatherWarps;
+    const long long per_warp = (n_items + n_warps - 1) / n_warps;
     const long long gw = static_cast<long long>(blockIdx.x) * kGatherWarps + warp;
-    const long long gstride = static_cast<long long>(gridDim.x) * kGatherWarps;
-    if (gw >= n_items) return;
-    const long long my_count = (n_items - gw + gstride - 1) / gstride;
+    const long long beg = gw * per_warp;
+    if (beg >= n_items) return;
+    const long long count = min(per_warp, n_items - beg);
 
+    auto prepare = [&](long long batch) {
+        const long long n = batch * 32 + lane;
+        if (n < count) {
+            const long long item = beg + n;
+            const long long row = item / pieces_per_row;
+            const int piece = static_cast<int>(item - row * pieces_per_row);
+            const long long off = static_cast<long long>(piece) * piece_bytes;
+            bool is_host;
+            const char* g = resolve_row(src, row, &is_host) + off;
+            const int k = static_cast<int>(n & 63);
+            m_src[warp][k] = reinterpret_cast<unsigned long long>(g);
+            m_dst[warp][k] = reinterpret_cast<unsigned long long>(out + row * out_stride + off);
+            m_bytes[warp][k] = static_cast<uint32_t>(min(static_cast<long long>(piece_bytes), row_bytes - off));
+        }
+    };
     auto issue_load = [&](long long n) {
-        const long long item = gw + n * gstride;
-        const long long row = item / pieces_per_row;
-        const int piece = static_cast<int>(item - row * pieces_per_row);
-        const long long off = static_cast<long long>(piece) * kSlotBytes;
-        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(kSlotBytes), row_bytes - off));
-        bool is_host;
-        const char* g = resolve_row(src, row, &is_host) + off;
-        const int slot = static_cast<int>(n % kSlots);
+        const int k = static_cast<int>(n & 63), slot = static_cast<int>(n % slots);
+        const uint32_t bytes = m_bytes[warp][k];
         mbar_expect_tx(&bars[warp][slot], bytes);
-        bulk_g2s(ring + slot * kSlotBytes, g, bytes, &bars[warp][slot]);
+        bulk_g2s(ring + slot * slot_bytes, reinterpret_cast<const void*>(m_src[warp][k]), bytes, &bars[warp][slot]);
     };
     auto issue_store = [&](long long n) {
-        const long long item = gw + n * gstride;
-        const long long row = item / pieces_per_row;
-        const int piece = static_cast<int>(item - row * pieces_per_row);
-        const long long off = static_cast<long long>(piece) * kSlotBytes;
-        const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(kSlotBytes), row_bytes - off));
-        const int slot = static_cast<int>(n % kSlots);
-        bulk_s2g(out + row * out_stride + off, ring + slot * kSlotBytes, bytes);
+        const int k = static_cast<int>(n & 63), slot = static_cast<int>(n % slots);
+        bulk_s2g(reinterpret_cast<void*>(m_dst[warp][k]), ring + slot * slot_bytes, m_bytes[warp][k]);
     };
 
-    const long long pre = min(static_cast<long long>(kSlots), my_count);
-    for (long long n = 0; n < pre; ++n) issue_load(n);
-    for (long long n = 0; n < my_count; ++n) {
-        const int slot = static_cast<int>(n % kSlots);
-        mbar_wait(&bars[warp][slot], static_cast<uint32_t>((n / kSlots) & 1));
-        issue_store(n);
-        // refill the slot of the PREVIOUS store once that store has drained its smem
-        if (n >= 1 && (n - 1) + kSlots < my_count) {
-            bulk_wait_read<1>();
-            issue_load((n - 1) + kSlots);
-        }
+    prepare(0);
+    prepare(1);
+    __syncwarp();
+    if (lane == 0) {
+        const long long pre = min(static_cast<long long>(slots), count);
+        for (long long n = 0; n < pre; ++n) issue_load(n);
     }
-    bulk_wait_all();
+    const long long n_batches = (count + 31) / 32;
+    for (long long b = 0; b < n_batches; ++b) {
+        if (lane == 0) {
+            const long long hi = min(count, b * 32 + 32);
+            for (long long n = b * 32; n < hi; ++n) {
+                const int slot = static_cast<int>(n % slots);
+                mbar_wait(&bars[warp][slot], static_cast<uint32_t>((n / slots) & 1));
+                issue_store(n);
+                // refill the slot of the PREVIOUS store once that store has drained its smem
+                if (n >= 1 && (n - 1) + slots < count) {
+                    bulk_wait_read<1>();
+                    issue_load((n - 1) + slots);
+                }
+            }
+        }
+        __syncwarp();
+        prepare(b + 2);  // reuses the metadata slots of batch b
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();
 }
 
 // generic fallback: one warp per row, 16-byte / 4-byte / 1-byte moves by alignment
@@ -139,17 +168,22 @@ static int launch_gather(const GatherSrc& src, void* out, int64_t out_stride, in
         DevInfo di;
         int rc = get_devinfo(&di);
         if (rc != DGLLB_OK) return rc;
-        const int pieces = static_cast<int>((row_bytes + kSlotBytes - 1) / kSlotBytes);
-        const size_t smem = static_cast<size_t>(kGatherWarps) * kSlots * kSlotBytes;
+        const int piece_bytes = static_cast<int>(row_bytes < kSlotBytes ? row_bytes : kSlotBytes);
+        const int pieces = static_cast<int>((row_bytes + piece_bytes - 1) / piece_bytes);
+        const int slot_bytes = (piece_bytes + 127) & ~127;
+        int slots = kGatherSmem / (kGatherWarps * slot_bytes);
+        if (slots > kMaxSlots) slots = kMaxSlots;
+        const size_t smem = static_cast<size_t>(kGatherWarps) * slots * slot_bytes;
         // opt in to >48 KB dynamic shared memory (idempotent)
         DGLLB_CUDA_TRY(cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
+                                            kGatherSmem));
         const long long items = n_rows * pieces;
-        long long blocks = (items + kGatherWarps - 1) / kGatherWarps;
-        const long long max_blocks = static_cast<long long>(di.sm_count);  // 128 KB smem => 1 CTA/SM
+        long long blocks = (items + kGatherWarps * 8 - 1) / (kGatherWarps * 8);  // >= 8 items per warp
+        const long long max_blocks = static_cast<long long>(di.sm_count);         // ~200 KB smem => 1 CTA/SM
         if (blocks > max_blocks) blocks = max_blocks;
+        if (blocks < 1) blocks = 1;
         gather_bulk_kernel<<<static_cast<unsigned>(blocks), kGatherWarps * 32, smem, st>>>(
-            src, static_cast<char*>(out), out_stride, n_rows, row_bytes, pieces);
+            src, static_cast<char*>(out), out_stride, n_rows, row_bytes, pieces, slots, slot_bytes, piece_bytes);
         DGLLB_LAUNCH_CHECK();
         return DGLLB_OK;
     }

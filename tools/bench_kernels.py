@@ -51,7 +51,7 @@ def report(name, shape, ms, nbytes, extra=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="full,gather,bin,gat,block")
+    ap.add_argument("--which", default="full,gather,bin,gat,block,gemm")
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
     which = set(args.which.split(","))
@@ -125,6 +125,32 @@ def main():
                 report("spmm_block0[%s]" % fam, "batch=%d n_dst=%d nnz=%d" % (batch, b0.num_dst, b0.num_edges()), ms, nbytes)
             os.environ.pop("DGLLB_SPMM_KERNEL", None)
         del table
+
+    if "gemm" in which:
+        try:
+            tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            tf = 1590.0
+        g = torch.Generator(device=dev).manual_seed(6)
+        for (M, Kd, Nd) in ((160000, 602, 256), (9539, 1204, 256), (2449029, 100, 256), (8192, 8192, 8192)):
+            a = torch.randn((M, Kd), device=dev, generator=g)
+            b = torch.randn((Kd, Nd), device=dev, generator=g)
+            out = torch.empty((M, Nd), device=dev)
+            flop = 2.0 * M * Kd * Nd
+            io_bytes = M * Kd * 4 + Kd * Nd * 4 + M * Nd * 4
+            for prec in ("bf16", "fp32"):
+                if prec == "fp32" and M * Kd * Nd > 4e11:
+                    continue
+                ms = timeit(lambda: K.gemm(a, b, out=out, precision=prec), args.iters)
+                print(json.dumps({"kernel": "gemm[%s]" % ("tcgen05 bf16" if prec == "bf16" else "simt fp32"),
+                                  "shape": "%dx%dx%d" % (M, Kd, Nd), "ms": round(ms, 4),
+                                  "TFLOPs": round(flop / ms / 1e9, 1), "frac_of_measured_bf16_peak": round(flop / ms / 1e9 / tf, 3),
+                                  "io_GBps": round(io_bytes / ms / 1e6, 1)}), flush=True)
+            ab, bb = a.to(torch.bfloat16), b.to(torch.bfloat16)
+            ms = timeit(lambda: torch.matmul(ab, bb), args.iters)
+            print(json.dumps({"kernel": "torch.matmul bf16 (cuBLAS comparator, operands pre-converted)",
+                              "shape": "%dx%dx%d" % (M, Kd, Nd), "ms": round(ms, 4), "TFLOPs": round(flop / ms / 1e9, 1)}), flush=True)
+            del a, b, out, ab, bb
 
     if "gat" in which:
         Np, E, Fp, _ = G.SHAPES["products"]
