@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true", help="skip the sampled-GraphSAGE training-epoch extra")
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -351,6 +352,38 @@ def main():
     e2e_ms = f0.elapsed_time(f1)
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- extra: sampled GraphSAGE TRAINING epoch (second half of BASELINE.json's metric) ------------------------
+    # 2-layer SAGE 602 -> 256 -> 41, fanout 25/10, batch 1024/GPU, Adam; every rank trains on its shard of the
+    # 153,756 train seeds (first 66 % of the nodes), gradients all-reduced as one flat buffer per step.
+    epoch = None
+    if not args.no_epoch:
+        import dgll_b200.nn as dnn
+        from dgll_b200 import train as T
+        torch.manual_seed(args.seed)
+        labels = torch.randint(0, 41, (N_NODES,), device=dev, generator=gen)
+        model = dnn.GraphSAGE(FEAT, HIDDEN, 41, 2, torch.relu, 0.0).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=0.003)
+        perm_e = torch.randperm(n_train, device=dev, generator=torch.Generator(device=dev).manual_seed(args.seed))
+        shard = perm_e[rank::world].contiguous()              # use_ddp-style split of the shuffled train seeds
+        res = {}
+        for prec in ("fp32", "bf16"):
+            T.sage_epoch(model, opt, table, labels, FEAT, row_ptr, col_idx, shard[:8 * BATCH], FANOUTS, BATCH,
+                         rng_seed=1, precision=prec)                                  # warm-up: 8 batches
+            barrier()
+            r_e2e = T.sage_epoch(model, opt, table, labels, FEAT, row_ptr, col_idx, shard, FANOUTS, BATCH,
+                                 rng_seed=2, precision=prec)                           # sampler in the loop
+            pre = T.make_batches(row_ptr, col_idx, shard, FANOUTS, BATCH, rng_seed=3)
+            barrier()
+            r_pre = T.sage_epoch(model, opt, table, labels, FEAT, batches=pre, precision=prec)
+            del pre
+            t = torch.tensor([r_e2e["time_s"], r_pre["time_s"]], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[prec] = {"epoch_s_sampler_in_loop": round(t[0].item(), 4), "epoch_s_presampled": round(t[1].item(), 4),
+                         "batches_per_gpu": r_e2e["n_batches"], "loss": round(r_e2e["loss"], 4)}
+        epoch = {"model": "GraphSAGE-mean 2-layer 602-256-41, fanout 25/10, batch 1024/GPU, Adam, fwd+bwd+step",
+                 "train_seeds": int(perm.numel()), "gemm": res}
+
     # ---- max over ranks ----------------------------------------------------------------------------------
     stats = torch.tensor([ms, e2e_ms, float(total_bytes), float(e2e_bytes), float(launches)], device=dev,
                          dtype=torch.float64)
@@ -384,7 +417,7 @@ def main():
                      "algorithmic_bytes_per_launch": k_bytes},
         "e2e": {"value": e2e_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches, "clocks": clk,
+        "gpu_launches": launches, "clocks": clk, "epoch": epoch,
     }
     if not args.no_cpu_baseline and world == 1:
         r = run_cpu_arm(6, 1, budget_s=24.0)

@@ -291,6 +291,7 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
         // degenerate / oversized: the SIMT path handles it exactly
         return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epi, accumulate, st);
     }
+    { DevInfo di_; int rc_ = get_devinfo(&di_); if (rc_ != DGLLB_OK) return rc_; }  // also configures the workspace pool
     const int Kp = static_cast<int>((K + kBK - 1) / kBK * kBK);
     const size_t bytes_a = (static_cast<size_t>(M) * Kp * 2 + 255) & ~static_cast<size_t>(255);
     const size_t bytes_b = (static_cast<size_t>(N) * Kp * 2 + 255) & ~static_cast<size_t>(255);

@@ -65,6 +65,7 @@ extern "C" int dgllb_gcn_fused_forward(const int* row_ptr, const int* col_idx, c
     if (N == 0 || H_dim == 0) return DGLLB_OK;
     DGLLB_REQUIRE(row_ptr && X && W && H && (total_nnz == 0 || (col_idx && values)),
                   "gcn_fused_forward: null pointer");
+    { DevInfo di_; int rc_ = get_devinfo(&di_); if (rc_ != DGLLB_OK) return rc_; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* S = nullptr;
     const long long ldS = (H_dim + 3) & ~3;  // keep rows 16-byte aligned for the vector path

@@ -93,6 +93,7 @@ extern "C" int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, con
         set_error("sample_neighbors: fanout %d > 32 not supported by this build", fanout);
         return DGLLB_ERR_UNSUPPORTED;
     }
+    { DevInfo di_; int rc_ = get_devinfo(&di_); if (rc_ != DGLLB_OK) return rc_; }  // also configures the workspace pool
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tb = 256;
     int* counts = nullptr;

@@ -66,6 +66,7 @@ extern "C" int dgllb_csr_transpose(const void* row_ptr, int row_ptr_is64, const 
     DGLLB_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "csr_transpose: negative size");
     DGLLB_REQUIRE(nnz < (1ll << 31) - 1 && n_rows < (1ll << 31) && n_cols < (1ll << 31),
                   "csr_transpose: sizes must fit int32 (nnz=%lld)", (long long)nnz);
+    { DevInfo di_; int rc_ = get_devinfo(&di_); if (rc_ != DGLLB_OK) return rc_; }  // also configures the workspace pool
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tb = 256;
     if (nnz == 0) {

@@ -4,7 +4,8 @@ from .conv import (GAT, GCN, GIN, GinConv, GraphConvolution, GraphSage, Neighbor
                    SpecialSpmmFunction, SpGAT, gatConv, gcnConv, sageConv, sparseGatConv)
 from .pooling import Pooling, maxPooling, meanPooling, sumPooling
 from .block_conv import GraphConv, SAGEConv
+from .models import BlockGCN, GraphSAGE
 
 __all__ = ["gcnConv", "GraphConvolution", "GCN", "sageConv", "NeighborAggregator", "GraphSage", "gatConv",
            "sparseGatConv", "SpecialSpmm", "SpecialSpmmFunction", "GAT", "SpGAT", "GinConv", "GIN", "sumPooling",
-           "meanPooling", "maxPooling", "Pooling", "GraphConv", "SAGEConv"]
+           "meanPooling", "maxPooling", "Pooling", "GraphConv", "SAGEConv", "BlockGCN", "GraphSAGE"]

@@ -19,13 +19,15 @@ from .. import backend as F
 from .. import ops
 
 
-def _graph_of(block, use_global=False):
+def _graph_of(block, use_global=False, n_table_rows=None):
+    """CsrGraph view of a block, cached on the block (no device read-back: n_src comes from the caller)."""
     key = "_csr_global" if use_global else "_csr"
     g = getattr(block, key, None)
     if g is None:
-        col = block.col_global if use_global else block.col
-        n_src = None if use_global else block.num_src_nodes()
-        g = ops.CsrGraph(block.row_ptr, col, n_src=n_src if n_src is not None else int(col.max().item()) + 1 if col.numel() else 0)
+        if use_global:
+            g = ops.CsrGraph(block.row_ptr, block.col_global, n_src=n_table_rows)
+        else:
+            g = ops.CsrGraph(block.row_ptr, block.col, n_src=block.num_src_nodes())
         setattr(block, key, g)
     return g
 
@@ -112,7 +114,7 @@ class SAGEConv(F.nn.Module):
         from the global table through ``block.col_global`` and only the dst rows are gathered."""
         n_dst = block.num_dst_nodes()
         if feat_table is not None:
-            g = _graph_of(block, use_global=True)
+            g = _graph_of(block, use_global=True, n_table_rows=feat_table.size(0))
             feat_src = feat_table
             feat_dst = ops.gather_rows(feat_table, block.src_ids[:n_dst])
         else:

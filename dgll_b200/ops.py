@@ -36,6 +36,7 @@ class CsrGraph:
     """CSR by destination row: ``row_ptr[n_dst+1]``, ``col[nnz]`` (source ids), optional ``values[nnz]``."""
 
     HEAVY_ROW = 4096  # rows longer than this get an nnz-split plan
+    PLAN_MIN_EDGES = 1 << 22
 
     def __init__(self, row_ptr, col, values=None, n_src=None):
         if not row_ptr.is_cuda:
@@ -73,7 +74,10 @@ class CsrGraph:
         """nnz-split schedule when the graph has very long rows (Reddit-shaped skew); None otherwise."""
         if self._plan is False:
             self._plan = None
-            if self.n_dst > 0 and float(self.degrees().max().item()) > self.HEAVY_ROW:
+            # only graphs big enough to have such rows are inspected (the check reads one scalar back = one sync
+            # per STATIC graph); sampled blocks never pay it
+            if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
+                    float(self.degrees().max().item()) > self.HEAVY_ROW:
                 self._plan = K.CsrPlan(self.row_ptr, chunk_edges=self.HEAVY_ROW)
         return self._plan
 
