@@ -60,22 +60,20 @@ class HaloExchange:
         """Bucketing + the two small exchanges.  Returns a dict reused by ``exchange`` (lets the caller overlap the id
         exchange of batch k+1 with the aggregation of batch k)."""
         ids = ids.to(torch.int64)
+        if self.world == 1:
+            self.stats["rows"] += ids.numel()
+            self.stats["calls"] += 1
+            return {"order": None, "send_split": None, "recv_split": None, "req": ids, "n": ids.numel()}
         owner = owner_of(ids, self.n_nodes, self.world)
         order = torch.sort(owner, stable=True).indices
         send_counts = torch.bincount(owner, minlength=self.world)
         recv_counts = torch.empty_like(send_counts)
-        if self.world > 1:
-            dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        else:
-            recv_counts.copy_(send_counts)
-        send_split = send_counts.tolist()
-        recv_split = recv_counts.tolist()
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        both = torch.stack([send_counts, recv_counts]).tolist()        # ONE device read-back per fetch
+        send_split, recv_split = both
         local_off = (ids - owner * self.part)[order].contiguous()
         req = torch.empty(sum(recv_split), dtype=torch.int64, device=ids.device)
-        if self.world > 1:
-            dist.all_to_all_single(req, local_off, recv_split, send_split, group=self.group)
-        else:
-            req.copy_(local_off)
+        dist.all_to_all_single(req, local_off, recv_split, send_split, group=self.group)
         self.stats["rows"] += ids.numel()
         self.stats["remote_rows"] += ids.numel() - send_split[self.rank]
         self.stats["calls"] += 1
@@ -83,6 +81,8 @@ class HaloExchange:
 
     def exchange(self, plan):
         rows_out = self.gather_fn(self.table, plan["req"])            # rows other ranks (and we) asked for
+        if plan["order"] is None:
+            return rows_out                                           # single rank: everything is local
         width = rows_out.shape[1:]
         recv = torch.empty((plan["n"],) + tuple(width), dtype=rows_out.dtype, device=rows_out.device)
         if self.world > 1:

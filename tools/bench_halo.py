@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: sampled GraphSAGE on a papers100M-shaped graph, features node-range partitioned across the
+GPUs of one box, halo feature rows exchanged with NCCL all-to-all (dgll_b200.parallel.HaloExchange).
+
+  python tools/bench_halo.py                                   # 1 GPU (everything local)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         tools/bench_halo.py [--scale 0.125] [--steps 60]
+
+Every rank: replicated topology (CSR by destination), its shard of the fp32 feature table [ceil(N/P), 128], its own
+seeds (local by destination).  One step = sample 25/10 blocks on the device -> bucket block0's source ids by owner ->
+all_to_all ids -> owners gather rows (TMA gather kernel) -> all_to_all rows -> 2-layer SAGE forward + backward on the
+aggregation kernels -> flat gradient all-reduce -> Adam.  Prints ONE JSON line on rank 0: whole-job seeds/s, ms per
+step (max over ranks, CUDA events), the stage breakdown and the remote-row fraction.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import dgll_b200.nn as dnn  # noqa: E402
+from dgll_b200 import graphs as G, ops, parallel as P  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N and nnz by this factor (1.0 = papers100M-shaped)")
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N0, NNZ0, F, C = G.SHAPES["papers100m"]
+    N = int(N0 * args.scale)
+    NNZ = int(NNZ0 * args.scale)
+    fanouts, hidden = (25, 10), 256
+
+    t0 = time.perf_counter()
+    if args.graph == "rmat":
+        row_ptr, col = G.rmat_csr(N, NNZ, seed=0, device=dev)
+    else:
+        # degree-14/15 control graph (papers100M's average in-degree is 14.5); same on every rank
+        gen = torch.Generator(device=dev).manual_seed(0)
+        deg = torch.full((N,), NNZ // N, dtype=torch.int64, device=dev)
+        deg[: NNZ - (NNZ // N) * N] += 1
+        row_ptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(deg, 0, out=row_ptr[1:])
+        del deg
+        col = torch.empty(NNZ, dtype=torch.int32, device=dev)
+        step = 1 << 28
+        for o in range(0, NNZ, step):
+            m = min(step, NNZ - o)
+            col[o:o + m] = torch.randint(0, N, (m,), device=dev, generator=gen, dtype=torch.int32)
+    lo, hi = P.local_range(rank, N, world)
+    table = G.feature_table(hi - lo, F, seed=100 + rank, device=dev)          # this rank's feature rows
+    labels = torch.randint(0, C, (N,), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    n_train = int(N * 1207179 / N0) if args.scale == 1.0 else int(N * 0.0109)
+    gs = torch.Generator(device=dev).manual_seed(7 + rank)
+    seeds_all = lo + torch.randperm(hi - lo, device=dev, generator=gs)[: max(n_train // world, args.batch * (args.steps + args.warmup))]
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    hx = P.HaloExchange(N, table)
+    torch.manual_seed(0)
+    model = dnn.GraphSAGE(F, hidden, C, 2, torch.relu, 0.0).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.003)
+    params = list(model.parameters())
+    ops.set_gemm_precision(args.precision)
+
+    def one_step(i, ev=None):
+        s = seeds_all[i * args.batch:(i + 1) * args.batch]
+        if ev: ev[0].record()
+        blocks = G.sample_blocks(row_ptr, col, s, fanouts, rng_seed=rank * 100003 + i)
+        if ev: ev[1].record()
+        x = hx.fetch(blocks[0].src_ids)                                          # [n_src0, F] incl. halo rows
+        if ev: ev[2].record()
+        logits = model(blocks, x)
+        loss = torch.nn.functional.cross_entropy(logits, labels[s])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        P.allreduce_gradients(params)
+        opt.step()
+        if ev: ev[3].record()
+        return blocks[0].num_src, blocks[0].num_edges()
+
+    for w in range(args.warmup):
+        one_step(w)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    hx.stats = {"rows": 0, "remote_rows": 0, "calls": 0}
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_src = n_edge = 0
+    for i in range(args.steps):
+        a, b = one_step(args.warmup + i, evs[i])
+        n_src += a
+        n_edge += b
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    stage = [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / args.steps for k in range(3)]
+    t = torch.tensor([ms] + stage, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = t[0].item()
+        seeds_per_s = world * args.batch * args.steps / (ms * 1e-3)
+        rows_per_step = hx.stats["rows"] / args.steps
+        remote = hx.stats["remote_rows"] / max(hx.stats["rows"], 1)
+        print(json.dumps({
+            "metric": "sampled GraphSAGE training throughput, papers100M-shaped, node-range partitioned features",
+            "value": seeds_per_s, "unit": "seeds/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps,
+            "epoch_s_extrapolated": (1207179 * args.scale) / seeds_per_s,
+            "stage_ms_max_over_ranks": {"sample": t[1].item(), "halo_exchange": t[2].item(), "fwd_bwd_step": t[3].item()},
+            "block0_src_rows_per_step": rows_per_step, "block0_edges_per_step": n_edge / args.steps,
+            "remote_row_fraction": remote,
+            "halo_bytes_in_per_gpu_per_step": rows_per_step * remote * F * 4,
+            "config": {"N": N, "nnz": NNZ, "F": F, "fanouts": list(fanouts), "batch_per_gpu": args.batch, "hidden": hidden,
+                       "graph": args.graph, "gemm": args.precision, "scale": args.scale, "setup_s": round(setup_s, 1)},
+            "scaling": "weak"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
