@@ -97,6 +97,73 @@ class HaloExchange:
     def fetch(self, ids):
         return self.exchange(self.plan(ids))
 
+    # ---- fixed-capacity variant: no host read-back, two collectives, static shapes -------------------------
+    def fetch_padded(self, ids, slack=1.3, cap=None):
+        """Same result as ``fetch`` without any device->host synchronisation: every rank sends each peer a
+        fixed-capacity id bucket (``cap`` = ceil(slack * max_rank len(ids) / world) rounded up to 128, agreed once; padded with -1) and
+        receives fixed-capacity row buckets back, so both all_to_all_single calls use equal splits known to the host.
+        Costs ``slack`` x the bandwidth; under the uniform node-range partition bucket sizes concentrate tightly
+        around len(ids)/world.  A bucket that would overflow sets ``self.overflow`` (device flag, checked by the
+        caller when convenient, e.g. once per epoch via ``check_overflow``); the overflowing rows come back as zeros."""
+        ids = ids.to(torch.int64)
+        n = ids.numel()
+        if self.world == 1:
+            self.stats["rows"] += n
+            self.stats["calls"] += 1
+            return self.gather_fn(self.table, ids)
+        W = self.world
+        if cap is None:
+            # the capacity must be IDENTICAL on every rank (equal-split collectives): agree on it once, from the
+            # largest request of the first call (one all-reduce + read-back), then keep it
+            if getattr(self, "_cap", None) is None:
+                nmax = torch.tensor([n], dtype=torch.int64, device=ids.device)
+                dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=self.group)
+                self._cap = (int(int(nmax.item()) * slack / W) + 128) // 128 * 128
+            cap = self._cap
+        dev = ids.device
+        owner = owner_of(ids, self.n_nodes, W)
+        order = torch.sort(owner, stable=True).indices
+        owner_s = owner[order]
+        counts = torch.bincount(owner, minlength=W)
+        start = torch.cumsum(counts, 0) - counts
+        pos = torch.arange(n, device=dev) - start[owner_s]                 # position inside the bucket
+        ok = pos < cap
+        if getattr(self, "overflow", None) is None:
+            self.overflow = torch.zeros((), dtype=torch.bool, device=dev)
+        self.overflow |= ~ok.all()
+        slot = owner_s * cap + pos.clamp(max=cap - 1)                        # flat index into [W, cap]
+        # (no boolean-mask indexing anywhere: it would read a size back to the host)
+        send_buf = torch.full((W * cap + 1,), -1, dtype=torch.int64, device=dev)
+        send_buf[torch.where(ok, slot, torch.full_like(slot, W * cap))] = (ids - owner * self.part)[order]
+        send_ids = send_buf[:W * cap]
+        recv_ids = torch.empty_like(send_ids)
+        dist.all_to_all_single(recv_ids, send_ids, group=self.group)
+        rows_out = self.gather_fn(self.table, recv_ids.clamp(min=0))        # padding gathers row 0 (discarded)
+        rows_in = torch.empty_like(rows_out)
+        dist.all_to_all_single(rows_in, rows_out, group=self.group)
+        got = self.gather_fn(rows_in, slot)                                  # bucketed order
+        got = got * ok.view((n,) + (1,) * (got.dim() - 1)).to(got.dtype)     # overflowed rows -> zeros
+        out = torch.empty_like(got)
+        out[order] = got
+        self.stats["rows"] += n
+        self.stats["remote_rows"] += n - n // W                              # expectation; exact counts stay on device
+        self.stats["calls"] += 1
+        return out
+
+    def set_bucket_capacity(self, max_ids_per_fetch, slack=1.3):
+        """Fix the per-peer bucket capacity of ``fetch_padded`` from a bound every rank agrees on (no collective)."""
+        self._cap = (int(max_ids_per_fetch * slack / self.world) + 128) // 128 * 128
+        return self._cap
+
+    def check_overflow(self):
+        """One read-back: True if any ``fetch_padded`` bucket overflowed since the last check."""
+        flag = getattr(self, "overflow", None)
+        if flag is None:
+            return False
+        v = bool(flag.item())
+        flag.zero_()
+        return v
+
 
 def allreduce_gradients(params, group=None, average=True):
     """Sum (and average) every ``.grad`` in ONE flat-buffer all-reduce (replaces the per-parameter loop of

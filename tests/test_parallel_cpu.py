@@ -47,10 +47,19 @@ def _halo_job(rank, world):
     hx = P.HaloExchange(n, full[lo:hi].clone(), gather_fn=_cpu_gather)
     g = torch.Generator().manual_seed(100 + rank)
     ok = True
+    hx.set_bucket_capacity(1003, slack=1.5)
     for m in (0, 1, 257, 1003):
         ids = torch.randperm(n, generator=g)[:m]
         out = hx.fetch(ids)
         ok = ok and out.shape == (m, f) and torch.equal(out, full[ids])
+        if m:
+            out2 = hx.fetch_padded(ids)
+            ok = ok and torch.equal(out2, full[ids]) and not hx.check_overflow()
+    # a deliberately tiny capacity must raise the overflow flag (and only zero the rows that did not fit)
+    ids = torch.randperm(n, generator=g)[:400]
+    out3 = hx.fetch_padded(ids, cap=16)
+    bad = (out3 != full[ids]).any(dim=1)
+    ok = ok and hx.check_overflow() and bool((out3[bad] == 0).all()) and int((~bad).sum()) >= 16
     # ids all owned by ONE rank (empty buckets elsewhere), duplicates allowed
     ids = torch.randint(0, hi - lo, (50,), generator=g) + (0 if rank else P.part_size(n, world))
     ids = ids.clamp(max=n - 1)

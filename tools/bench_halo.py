@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"])
+    ap.add_argument("--halo", default="exact", choices=["padded", "exact"],
+                    help="exact = counts exchanged first (one read-back); padded = fixed-capacity buckets, no host sync "
+                         "(measured slower on this host-bound step: profiles/r01_halo_2gpu_padded.json)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -86,7 +89,7 @@ def main():
         if ev: ev[0].record()
         blocks = G.sample_blocks(row_ptr, col, s, fanouts, rng_seed=rank * 100003 + i)
         if ev: ev[1].record()
-        x = hx.fetch(blocks[0].src_ids)                                          # [n_src0, F] incl. halo rows
+        x = hx.fetch_padded(blocks[0].src_ids) if args.halo == "padded" else hx.fetch(blocks[0].src_ids)
         if ev: ev[2].record()
         logits = model(blocks, x)
         loss = torch.nn.functional.cross_entropy(logits, labels[s])
@@ -134,7 +137,7 @@ def main():
             "remote_row_fraction": remote,
             "halo_bytes_in_per_gpu_per_step": rows_per_step * remote * F * 4,
             "config": {"N": N, "nnz": NNZ, "F": F, "fanouts": list(fanouts), "batch_per_gpu": args.batch, "hidden": hidden,
-                       "graph": args.graph, "gemm": args.precision, "scale": args.scale, "setup_s": round(setup_s, 1)},
+                       "graph": args.graph, "gemm": args.precision, "halo": args.halo, "halo_overflow": hx.check_overflow(), "scale": args.scale, "setup_s": round(setup_s, 1)},
             "scaling": "weak"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
