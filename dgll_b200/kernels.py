@@ -212,6 +212,43 @@ def gather_rows_cached(cache_table, host_table, ids, gpu_flag, localid2cacheid, 
     return out
 
 
+def gather_rows_sharded(shard_ptrs, rows_per_shard, stride_bytes, ids, width, dtype, out=None):
+    """``out[i] = shard[id // rows_per_shard][id % rows_per_shard]`` — ``shard_ptrs`` is a device int64 tensor of
+    device pointers (local shard + peer shards mapped over NVLink, see ``parallel.PeerShardedTable``)."""
+    _need_cuda(shard_ptrs, ids, out)
+    if ids.dtype not in (torch.int32, torch.int64):
+        raise TypeError("ids must be int32/int64")
+    ids = ids.contiguous()
+    esz = torch.empty(0, dtype=dtype).element_size()
+    if out is None:
+        out = torch.empty((ids.numel(), width), dtype=dtype, device=ids.device)
+    check(lib().dgllb_gather_rows_sharded(_p(shard_ptrs), shard_ptrs.numel(), int(rows_per_shard), int(stride_bytes),
+                                          _p(ids), int(ids.dtype == torch.int64), _p(out), out.stride(0) * esz,
+                                          ids.numel(), width * esz, _stream()), "gather_rows_sharded")
+    return out
+
+
+def ipc_export(t):
+    """(64-byte handle, offset) of the device allocation holding tensor ``t``."""
+    _need_cuda(t)
+    buf = (ctypes.c_ubyte * 64)()
+    off = ctypes.c_int64()
+    check(lib().dgllb_ipc_export(_p(t), buf, ctypes.byref(off)), "ipc_export")
+    return bytes(buf), off.value
+
+
+def ipc_import(handle, offset):
+    """Device pointer (int) of a peer allocation mapped into this process."""
+    buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    out = ctypes.c_void_p()
+    check(lib().dgllb_ipc_import(buf, int(offset), ctypes.byref(out)), "ipc_import")
+    return out.value
+
+
+def ipc_release(ptr, offset):
+    check(lib().dgllb_ipc_release(ctypes.c_void_p(ptr), int(offset)), "ipc_release")
+
+
 def gemm(a, b, bias=None, relu=False, elu=False, trans_a=False, trans_b=False, out=None, accumulate=False,
          precision="fp32"):
     """Dense transform ``op(a) @ op(b) (+bias)``: ``fp32`` = exact SIMT path, ``bf16`` = tcgen05 tensor cores."""

@@ -165,6 +165,57 @@ class HaloExchange:
         return v
 
 
+class PeerShardedTable:
+    """The node-range-partitioned feature table of one NVSwitch box, readable in place from every GPU.
+
+    Each rank passes its own shard ``[ceil(N/P), ld]``; the constructor exchanges CUDA-IPC handles once
+    (``all_gather_object``), maps the peers' shards and keeps a device array of the P shard pointers.  ``fetch(ids)``
+    is then ONE kernel launch (``dgllb_gather_rows_sharded``): remote rows are pulled over NVLink by the gather kernel
+    itself — no bucketing, no all_to_all, no host read-back.  All shards must have the same row stride; the last
+    shard may be shorter.  (Same result as ``HaloExchange.fetch``; this is the B200-native mechanism.)"""
+
+    def __init__(self, n_nodes, local_table, group=None):
+        from . import kernels as K
+        self._K = K
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_nodes, self.part = n_nodes, part_size(n_nodes, self.world)
+        lo, hi = local_range(self.rank, n_nodes, self.world)
+        if local_table.size(0) != hi - lo or not local_table.is_cuda or local_table.stride(1) != 1:
+            raise ValueError("rank %d must hold rows [%d, %d) of the table as a row-major CUDA tensor" % (self.rank, lo, hi))
+        self.table = local_table
+        self.width, self.dtype = local_table.size(1), local_table.dtype
+        self.stride_bytes = local_table.stride(0) * local_table.element_size()
+        self._mapped = []
+        ptrs = [0] * self.world
+        ptrs[self.rank] = local_table.data_ptr()
+        if self.world > 1:
+            handle, off = K.ipc_export(local_table)
+            infos = [None] * self.world
+            dist.all_gather_object(infos, (handle, off, self.stride_bytes), group=group)
+            for r, (h, o, sb) in enumerate(infos):
+                if sb != self.stride_bytes:
+                    raise ValueError("all shards must share one row stride")
+                if r != self.rank:
+                    ptrs[r] = K.ipc_import(h, o)
+                    self._mapped.append((ptrs[r], o))
+            dist.barrier(group=group)
+        self.shard_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=local_table.device)
+        self.stats = {"rows": 0, "calls": 0}
+
+    def fetch(self, ids, out=None):
+        self.stats["rows"] += ids.numel()
+        self.stats["calls"] += 1
+        return self._K.gather_rows_sharded(self.shard_ptrs, self.part, self.stride_bytes, ids, self.width, self.dtype,
+                                           out=out)
+
+    def close(self):
+        for ptr, off in self._mapped:
+            self._K.ipc_release(ptr, off)
+        self._mapped = []
+
+
 def allreduce_gradients(params, group=None, average=True):
     """Sum (and average) every ``.grad`` in ONE flat-buffer all-reduce (replaces the per-parameter loop of
     GPU Accelerator/MQGCN.py:55-67 — 4-6 latency-bound NCCL calls per step — and DDP buckets, :141-144)."""

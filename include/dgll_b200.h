@@ -182,6 +182,28 @@ int dgllb_gather_rows_cached(const void* cache_table, int64_t cache_stride_bytes
                              void* out, int64_t out_stride_bytes, int64_t n_rows,
                              int64_t row_bytes, int64_t* miss_count, void* stream);
 
+/*
+ * Feature table sharded by NODE RANGE over the GPUs of one NVSwitch box (shard s holds rows
+ * [s*rows_per_shard, (s+1)*rows_per_shard)), read in place over NVLink:
+ *   out[i, 0:row_bytes) = shard_ptrs[id / rows_per_shard][(id % rows_per_shard) * stride_bytes ...]
+ * shard_ptrs is a DEVICE array of n_shards device pointers (the local shard + peer shards mapped with
+ * dgllb_ipc_import).  Replaces, for the partitioned table, the gather of dgll/data/dgraph.py:105 and the
+ * host/RPC feature fetch of FeatureCache/storage.py:101-126 — no collective, no host read-back
+ * (SURVEY.md §8 e "P2P-map all shards and let the gather kernel issue remote 128-bit loads").
+ */
+int dgllb_gather_rows_sharded(const void* const* shard_ptrs, int n_shards, int64_t rows_per_shard,
+                              int64_t stride_bytes, const void* ids, int ids_is64, void* out,
+                              int64_t out_stride_bytes, int64_t n_rows, int64_t row_bytes, void* stream);
+
+/*
+ * CUDA IPC plumbing for the above.  export: 64-byte handle of the allocation containing dev_ptr + the offset of
+ * dev_ptr inside it (caching allocators sub-allocate).  import: map a peer's allocation (peer access enabled
+ * lazily) and return the pointer at `offset`.  release: unmap (pass the same offset).
+ */
+int dgllb_ipc_export(const void* dev_ptr, unsigned char* handle64, int64_t* offset);
+int dgllb_ipc_import(const unsigned char* handle64, int64_t offset, void** dev_ptr_out);
+int dgllb_ipc_release(void* dev_ptr, int64_t offset);
+
 /* -------------------------------------------------- dense transform X.W -- */
 
 /*

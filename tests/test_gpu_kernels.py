@@ -620,3 +620,37 @@ def test_layers_run_on_tensor_core_path(K):
     finally:
         ops.set_gemm_precision("fp32")
     assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= BF16_TOL
+
+
+# ---------------------------------------------------- sharded / peer gather --
+@pytest.mark.parametrize("F,dtype", [(128, torch.float32), (602, torch.float32), (64, torch.bfloat16), (3, torch.float32)])
+def test_gather_rows_sharded_bit_exact(K, F, dtype):
+    """Node-range sharded table read through a device array of shard pointers (here all shards live on one GPU; on
+    the 8-GPU box the same kernel dereferences peer pointers mapped with dgllb_ipc_import)."""
+    g = torch.Generator(device="cuda").manual_seed(F)
+    n, P = 10007, 4
+    part = (n + P - 1) // P
+    ld = (F + 3) // 4 * 4 if dtype == torch.float32 else (F + 7) // 8 * 8
+    full = torch.randn((n, ld), device="cuda", generator=g).to(dtype)
+    shards = [full[r * part:min(n, (r + 1) * part)].clone() for r in range(P)]
+    ptrs = torch.tensor([s.data_ptr() for s in shards], dtype=torch.int64, device="cuda")
+    for idt in (torch.int64, torch.int32):
+        ids = torch.randint(0, n, (5000,), device="cuda", generator=g).to(idt)
+        out = K.gather_rows_sharded(ptrs, part, ld * full.element_size(), ids, ld, dtype)
+        assert torch.equal(out, full[ids.long()])
+    from dgll_b200.parallel import PeerShardedTable
+    t = PeerShardedTable(n, full)            # world size 1: the single shard is the local table
+    ids = torch.randint(0, n, (777,), device="cuda", generator=g)
+    assert torch.equal(t.fetch(ids), full[ids])
+
+
+def test_ipc_export_import_roundtrip_same_process(K):
+    """The IPC handle of a tensor's allocation + offset names the same bytes (cudaIpcOpenMemHandle cannot be opened in
+    the exporting process, so only the export side and the offset arithmetic are checked here; the cross-process
+    path runs in tools/bench_halo.py --halo peer on >= 2 GPUs)."""
+    big = torch.empty(1 << 20, device="cuda")
+    view = big[12345:]
+    h, off = K.ipc_export(view)
+    assert len(h) == 64 and off >= 12345 * 4 and off % 4 == 0
+    h2, off2 = K.ipc_export(big)
+    assert h2 == h and off - off2 == 12345 * 4

@@ -36,9 +36,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"])
-    ap.add_argument("--halo", default="exact", choices=["padded", "exact"],
-                    help="exact = counts exchanged first (one read-back); padded = fixed-capacity buckets, no host sync "
-                         "(measured slower on this host-bound step: profiles/r01_halo_2gpu_padded.json)")
+    ap.add_argument("--halo", default="peer", choices=["padded", "exact", "peer"],
+                    help="peer = shards mapped over NVLink (CUDA IPC), ONE gather kernel pulls remote rows; exact = NCCL "
+                         "all_to_all with counts exchanged first; padded = NCCL with fixed-capacity buckets, no host sync")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -77,7 +77,7 @@ def main():
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
 
-    hx = P.HaloExchange(N, table)
+    hx = P.PeerShardedTable(N, table) if args.halo == "peer" else P.HaloExchange(N, table)
     torch.manual_seed(0)
     model = dnn.GraphSAGE(F, hidden, C, 2, torch.relu, 0.0).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=0.003)
@@ -89,7 +89,7 @@ def main():
         if ev: ev[0].record()
         blocks = G.sample_blocks(row_ptr, col, s, fanouts, rng_seed=rank * 100003 + i)
         if ev: ev[1].record()
-        x = hx.fetch_padded(blocks[0].src_ids) if args.halo == "padded" else hx.fetch(blocks[0].src_ids)
+        x = hx.fetch_padded(blocks[0].src_ids) if args.halo == "padded" else hx.fetch(blocks[0].src_ids)  # peer: ONE kernel
         if ev: ev[2].record()
         logits = model(blocks, x)
         loss = torch.nn.functional.cross_entropy(logits, labels[s])
@@ -106,6 +106,17 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     hx.stats = {"rows": 0, "remote_rows": 0, "calls": 0}
+    verified = None
+    if args.halo == "peer" and world > 1:
+        # bit-exact cross-check of the NVLink peer gather against the NCCL all-to-all exchange on one real batch
+        blocks = G.sample_blocks(row_ptr, col, seeds_all[:args.batch], fanouts, rng_seed=12345 + rank)
+        a = hx.fetch(blocks[0].src_ids)
+        b = P.HaloExchange(N, table).fetch(blocks[0].src_ids)
+        ok = torch.tensor([int(torch.equal(a, b))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        verified = bool(ok.item())
+        assert verified, "peer gather and NCCL halo exchange disagree"
+    hx_overflow = (lambda: hx.check_overflow()) if hasattr(hx, "check_overflow") else (lambda: False)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -127,7 +138,7 @@ def main():
         ms = t[0].item()
         seeds_per_s = world * args.batch * args.steps / (ms * 1e-3)
         rows_per_step = hx.stats["rows"] / args.steps
-        remote = hx.stats["remote_rows"] / max(hx.stats["rows"], 1)
+        remote = (hx.stats["remote_rows"] / max(hx.stats["rows"], 1)) if args.halo != "peer" else (world - 1) / world
         print(json.dumps({
             "metric": "sampled GraphSAGE training throughput, papers100M-shaped, node-range partitioned features",
             "value": seeds_per_s, "unit": "seeds/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps,
@@ -137,7 +148,7 @@ def main():
             "remote_row_fraction": remote,
             "halo_bytes_in_per_gpu_per_step": rows_per_step * remote * F * 4,
             "config": {"N": N, "nnz": NNZ, "F": F, "fanouts": list(fanouts), "batch_per_gpu": args.batch, "hidden": hidden,
-                       "graph": args.graph, "gemm": args.precision, "halo": args.halo, "halo_overflow": hx.check_overflow(), "scale": args.scale, "setup_s": round(setup_s, 1)},
+                       "graph": args.graph, "gemm": args.precision, "halo": args.halo, "halo_overflow": hx_overflow(), "peer_vs_nccl_bit_exact": verified, "scale": args.scale, "setup_s": round(setup_s, 1)},
             "scaling": "weak"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
