@@ -3,6 +3,16 @@
 #pragma once
 #include "common.cuh"
 
+// nnz-split schedule of a static CSR (opaque to C callers, include/dgll_b200.h)
+struct dgllb_csr_plan {
+    int chunk_edges;
+    long long n_rows;
+    long long n_heavy_rows;
+    long long n_items;
+    int* heavy_rows;  // device: rows longer than chunk_edges
+    int2* items;      // device: (row, chunk index) for every chunk of every heavy row
+};
+
 namespace dgllb {
 
 struct SpmmParams {

@@ -487,14 +487,6 @@ __global__ void plan_fill_kernel(const void* row_ptr, int rp64, long long n_rows
 
 }  // namespace dgllb
 
-struct dgllb_csr_plan {
-    int chunk_edges;
-    long long n_rows;
-    long long n_heavy_rows;
-    long long n_items;
-    int* heavy_rows;  // device
-    int2* items;      // device
-};
 
 using namespace dgllb;
 

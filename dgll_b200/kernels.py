@@ -360,7 +360,7 @@ def binarize_pack(x):
     return packed
 
 
-def bin_spmm_csr(row_ptr, col_idx, packed, F, mode="count", n_dst=None):
+def bin_spmm_csr(row_ptr, col_idx, packed, F, mode="count", n_dst=None, plan=None):
     """Binarized aggregation: ``count`` (int32), ``sum`` (+-1 sum, fp32) or ``mean`` (+-1 mean, fp32)."""
     _need_cuda(row_ptr, col_idx, packed)
     rp, is64 = _rowptr(row_ptr)
@@ -370,7 +370,7 @@ def bin_spmm_csr(row_ptr, col_idx, packed, F, mode="count", n_dst=None):
     md = {"count": 0, "sum": 1, "mean": 2}[mode]
     out = torch.empty((n_dst, F), dtype=torch.int32 if md == 0 else torch.float32, device=packed.device)
     check(lib().dgllb_bin_spmm_csr(_p(rp), is64, _p(col), _p(packed), packed.size(1), _p(out), F, n_dst, F, md,
-                                   _stream()), "bin_spmm_csr")
+                                   plan._h if plan is not None else None, _stream()), "bin_spmm_csr")
     return out
 
 

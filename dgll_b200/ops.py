@@ -81,6 +81,15 @@ class CsrGraph:
                 self._plan = K.CsrPlan(self.row_ptr, chunk_edges=self.HEAVY_ROW)
         return self._plan
 
+    def bin_plan(self):
+        """nnz-split for the binarized kernel (one warp per 1,024 edges of a long row; integer atomics, exact)."""
+        if getattr(self, "_bin_plan", False) is False:
+            self._bin_plan = None
+            if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
+                    float(self.degrees().max().item()) > 1024:
+                self._bin_plan = K.CsrPlan(self.row_ptr, chunk_edges=1024)
+        return self._bin_plan
+
     def transpose(self):
         """CsrGraph of A^T (values carried along); ``perm[e_T] = e`` kept for per-edge gradients."""
         if self._t is None:
@@ -297,6 +306,20 @@ def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False
         out = _GatFn.apply(wh, el, er, graph, heads, slope, mode)
         return torch.nn.functional.elu(out) if elu else out
     return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst)
+
+
+# -------------------------------------------------------------- binarized ---
+def binarized_aggregate(adj, x=None, packed=None, F=None, mode="mean"):
+    """Binarized neighbourhood aggregation (README.md:11; semantics SURVEY.md §8 a18): features are reduced to their
+    sign bit (``x >= 0``), bit-packed 32 per word, and aggregated with the bit-sliced popcount kernel.
+    ``mode``: 'count' (int32 #neighbours with the bit set), 'sum' / 'mean' of the +-1 values (fp32).
+    Pass ``packed`` (from ``kernels.binarize_pack``) to reuse a packed table across layers/steps.  Forward only."""
+    graph = as_csr(adj, binary=True)
+    if packed is None:
+        packed = K.binarize_pack(x)
+        F = x.size(1)
+    plan = graph.bin_plan()
+    return K.bin_spmm_csr(graph.row_ptr, graph.col, packed, F, mode=mode, n_dst=graph.n_dst, plan=plan)
 
 
 # ----------------------------------------------------------------- gather ---

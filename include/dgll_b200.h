@@ -281,12 +281,14 @@ int dgllb_binarize_pack(const float* X, int64_t ldx, uint32_t* packed,
  * cnt[i,f] = sum_{e in row i} bit f of packed[col_idx[e]]          (int32, exact)
  * out modes: 0 = counts as int32; 1 = float sum of +-1 (2*cnt - deg);
  *            2 = float mean of +-1 ((2*cnt - deg)/deg, empty row -> 0).
- * Popcount formulation: 32 neighbours' words are bit-transposed across the
- * warp and __popc'd into per-feature counters.
+ * Bit-sliced formulation: lane l owns packed word l of every neighbour; counts are kept in
+ * carry-save bit planes (32 features per bitwise op) and scattered feature-major with shuffles.
  */
 int dgllb_bin_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
                        const uint32_t* packed, int64_t words_per_row, void* out,
-                       int64_t ldo, int64_t n_dst, int F, int out_mode, void* stream);
+                       int64_t ldo, int64_t n_dst, int F, int out_mode,
+                       const dgllb_csr_plan* plan /* optional nnz-split of long rows; exact (integer atomics) */,
+                       void* stream);
 
 /* ------------------------------------------------ sampling / blocks ------ */
 

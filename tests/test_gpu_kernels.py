@@ -264,6 +264,12 @@ def test_binarize_and_bin_spmm_bit_exact(K, F):
     with np.errstate(divide="ignore", invalid="ignore"):
         ref_m = np.where(deg > 0, (2.0 * ref_cnt - deg) / deg, 0.0)
     assert rel_err(m, ref_m) <= FP32_TOL
+    # nnz-split plan for long rows: integer atomics, still bit-exact
+    plan = K.CsrPlan(dev(rp), chunk_edges=200)
+    assert plan.n_heavy_rows >= 1
+    assert np.array_equal(K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="count", plan=plan).cpu().numpy(), ref_cnt)
+    assert np.array_equal(K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="sum", plan=plan).cpu().numpy(), s)
+    assert rel_err(K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="mean", plan=plan).cpu().numpy(), ref_m) <= FP32_TOL
     # cross-check with the fp32 kernel on sign(x): same aggregation, different formulation
     sx = np.where(x >= 0, 1.0, -1.0).astype(np.float32)
     agg = K.spmm_csr(dev(rp), dev(col), dev(sx), reduce="sum").cpu().numpy()

@@ -101,12 +101,16 @@ def main():
         packed = K.binarize_pack(x[:, :F])
         wpr = packed.size(1)
         nbytes = NNZ * (4 + 4 * wpr) + N * (4 * F + 8)
-        ms = timeit(lambda: K.bin_spmm_csr(rp, col, packed, F, mode="mean"), args.iters)
-        report("bin_spmm_csr", "F=%d words/row=%d" % (F, wpr), ms, nbytes)
+        ms_np = timeit(lambda: K.bin_spmm_csr(rp, col, packed, F, mode="mean"), args.iters)
+        report("bin_spmm_csr[no plan]", "F=%d words/row=%d" % (F, wpr), ms_np, nbytes)
+        bplan = K.CsrPlan(rp, chunk_edges=1024)
+        ms = timeit(lambda: K.bin_spmm_csr(rp, col, packed, F, mode="mean", plan=bplan), args.iters)
+        report("bin_spmm_csr[plan 1024]", "F=%d words/row=%d" % (F, wpr), ms, nbytes, {"chunks": bplan.n_chunks})
         ms_pack = timeit(lambda: K.binarize_pack(x[:, :F]), args.iters)
         report("binarize_pack", "N=%d F=%d" % (N, F), ms_pack, N * (F * 4 + wpr * 4))
         out = torch.empty((N, 604), device=dev)[:, :F]
-        ms32 = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=F), args.iters)
+        plan32 = K.CsrPlan(rp, chunk_edges=4096)
+        ms32 = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=F, plan=plan32), args.iters)
         report("spmm_full_graph fp32 (C4 comparator)", "F=%d" % F, ms32, NNZ * (4 + F * 4) + N * (F * 4 + 8),
                {"speedup_binarized_vs_fp32": round(ms32 / ms, 2)})
         del x, packed, out
