@@ -19,6 +19,7 @@
 // Algorithmic bytes fwd: nnz*(4 + F*4 + heads*4) + n_dst*(F*4 + heads*4 + r).
 #include "common.cuh"
 #include "internal.cuh"
+#include <stdlib.h>
 
 namespace dgllb {
 
@@ -181,6 +182,156 @@ gat_forward_kernel(const GatParams p) {
     }
 }
 
+
+// ------------------------------------------------- whole-row forward kernel --
+// One WARP per destination row, all heads at once (heads <= 4, heads*D <= 128*NV floats, D % 4 == 0): lane l owns the
+// 16-byte vectors l, l+32, ... of the concatenated head outputs, so a source row (e.g. 4 x 64 floats = 1 KB) is
+// fetched by NV coalesced LDG.128 per lane and its column id / score work is done ONCE per edge instead of once per
+// (edge, head) as in gat_forward_kernel (profiles/r01_gat_forward.txt: 11.0 G warp instructions, latency bound).
+// Per 32-edge chunk: lane e scores edge e for every head (er[col] fetched as one vector), the chunk's softmax
+// statistics are 2 warp reductions per head, scores and column ids are parked in shared memory and every lane reads
+// back the weight of ITS head with a broadcast LDS.  Column ids / er values of the next chunks are prefetched.
+constexpr int kRowWarps = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(kRowWarps * 32)
+gat_forward_row_kernel(const GatParams p) {
+    __shared__ int s_c[kRowWarps][32];
+    __shared__ float s_p[kRowWarps][32][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = static_cast<long long>(blockIdx.x) * kRowWarps + warp;
+    if (row >= p.n_dst) return;
+    const int H = p.heads, FD = p.heads * p.D;
+    const long long beg = gat_rp(p.row_ptr, p.rp64, row), end = gat_rp(p.row_ptr, p.rp64, row + 1);
+
+    // this lane's vectors and the head each one belongs to
+    int hsel[NV];
+    bool von[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * 32 + lane) * 4;
+        von[i] = c0 < FD;
+        hsel[i] = von[i] ? c0 / p.D : 0;
+    }
+    float el_i[4], m[4], l[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        el_i[h] = h < H ? __ldg(p.el + row * p.ld_e + h) : 0.f;
+        m[h] = -INFINITY;
+        l[h] = 0.f;
+    }
+    float acc[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[i][a] = 0.f;
+
+    auto load_er = [&](int c, float* dst) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) dst[h] = h < H ? __ldg(p.er + static_cast<long long>(c) * p.ld_e + h) : 0.f;
+    };
+    int c_cur = 0, c_nxt = 0;
+    float er_cur[4] = {0.f, 0.f, 0.f, 0.f};
+    if (beg + lane < end) {
+        c_cur = __ldg(p.col + beg + lane);
+        load_er(c_cur, er_cur);
+    }
+    if (beg + 32 + lane < end) c_nxt = __ldg(p.col + beg + 32 + lane);
+
+    for (long long e0 = beg; e0 < end; e0 += 32) {
+        const int n = static_cast<int>(min(32ll, end - e0));
+        float er_nxt[4] = {0.f, 0.f, 0.f, 0.f};
+        if (e0 + 32 + lane < end) load_er(c_nxt, er_nxt);
+        int c_nxt2 = 0;
+        if (e0 + 64 + lane < end) c_nxt2 = __ldg(p.col + e0 + 64 + lane);
+
+        float corr[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            corr[h] = 1.f;
+            if (h < H) {
+                float sc = -INFINITY;
+                if (lane < n) {
+                    float z = el_i[h] + er_cur[h];
+                    z = z > 0.f ? z : p.slope * z;
+                    sc = p.sign * z;
+                }
+                const float m_new = fmaxf(m[h], warp_max(sc));
+                corr[h] = (m[h] == -INFINITY) ? 0.f : expf(m[h] - m_new);
+                const float pe = (lane < n) ? expf(sc - m_new) : 0.f;
+                l[h] = l[h] * corr[h] + warp_sum(pe);
+                m[h] = m_new;
+                s_p[warp][lane][h] = pe;
+            }
+        }
+        s_c[warp][lane] = c_cur;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float cr = hsel[i] == 0 ? corr[0] : hsel[i] == 1 ? corr[1] : hsel[i] == 2 ? corr[2] : corr[3];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[i][a] *= cr;
+        }
+        for (int k = 0; k < n; k += 4) {
+            float4 raw[4][NV];
+            float w[4][NV];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool on = k + u < n;
+                const int c = s_c[warp][(k + u) & 31];
+                const float* src = p.Wh + static_cast<long long>(c) * p.ldw + lane * 4;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (on && von[i]) {
+                        raw[u][i] = ldg_nc_f4(src + i * 128);
+                        w[u][i] = s_p[warp][(k + u) & 31][hsel[i]];
+                    } else {
+                        raw[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        w[u][i] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    acc[i][0] = fmaf(w[u][i], raw[u][i].x, acc[i][0]);
+                    acc[i][1] = fmaf(w[u][i], raw[u][i].y, acc[i][1]);
+                    acc[i][2] = fmaf(w[u][i], raw[u][i].z, acc[i][2]);
+                    acc[i][3] = fmaf(w[u][i], raw[u][i].w, acc[i][3]);
+                }
+        }
+        __syncwarp();  // everyone is done with s_c / s_p before the next chunk overwrites them
+        c_cur = c_nxt;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) er_cur[h] = er_nxt[h];
+        c_nxt = c_nxt2;
+    }
+
+    if (lane < H) {
+        float mm = m[0], ll = l[0];
+#pragma unroll
+        for (int h = 1; h < 4; ++h)
+            if (lane == h) { mm = m[h]; ll = l[h]; }
+        if (p.row_max) p.row_max[row * H + lane] = mm;
+        if (p.row_sum) p.row_sum[row * H + lane] = ll;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (!von[i]) continue;
+        const float lh = hsel[i] == 0 ? l[0] : hsel[i] == 1 ? l[1] : hsel[i] == 2 ? l[2] : l[3];
+        const float inv = lh > 0.f ? 1.f / lh : 0.f;
+        float v[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float t = acc[i][a] * inv;
+            if (p.epi & DGLLB_EPI_RELU) t = fmaxf(t, 0.f);
+            if (p.epi & DGLLB_EPI_ELU) t = t > 0.f ? t : expm1f(t);
+            v[a] = t;
+        }
+        stg_cs_f4(p.out + row * p.ldo + (i * 32 + lane) * 4, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
 
 // ------------------------------------------------------------- backward --
 struct GatBwdParams {
@@ -420,6 +571,21 @@ static int launch_gat_bwd(const GatBwdParams& p, cudaStream_t st) {
 
 template <int VE>
 static int launch_gat_fwd(GatParams& p, cudaStream_t st) {
+    // whole-row kernel: all heads of a row in one warp (vector path, <= 4 heads, 64 < heads*D <= 512).  Measured on
+    // the products-shaped graph (4 x 64): 48.6 ms against 42.5 ms for the per-(row, head) kernel below — 4x fewer
+    // instructions do not help a latency-bound loop — so it only runs when pinned with DGLLB_GAT_KERNEL=row.
+    const int FD = p.heads * p.D;
+    const char* force = getenv("DGLLB_GAT_KERNEL");
+    if (VE == 4 && p.heads <= 4 && FD > 64 && FD <= 512 && force && force[0] == 'r') {
+        const long long blocks = (p.n_dst + kRowWarps - 1) / kRowWarps;
+        DGLLB_REQUIRE(blocks < (1ll << 31), "gat_forward: grid too large");
+        const unsigned g = static_cast<unsigned>(blocks);
+        if (FD <= 128) gat_forward_row_kernel<1><<<g, kRowWarps * 32, 0, st>>>(p);
+        else if (FD <= 256) gat_forward_row_kernel<2><<<g, kRowWarps * 32, 0, st>>>(p);
+        else gat_forward_row_kernel<4><<<g, kRowWarps * 32, 0, st>>>(p);
+        DGLLB_LAUNCH_CHECK();
+        return DGLLB_OK;
+    }
     int lanes = 32;
     if (VE > 1 && p.D <= 8 * VE) lanes = 8;
     else if (VE > 1 && p.D <= 16 * VE) lanes = 16;

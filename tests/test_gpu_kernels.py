@@ -277,7 +277,7 @@ def test_binarize_and_bin_spmm_bit_exact(K, F):
 
 
 # ------------------------------------------------------------------ GAT -----
-@pytest.mark.parametrize("heads,D", [(4, 64), (1, 47), (4, 16), (2, 8), (1, 256), (3, 5)])
+@pytest.mark.parametrize("heads,D", [(4, 64), (1, 47), (4, 16), (2, 8), (1, 256), (3, 5), (4, 128), (2, 48), (3, 100)])
 @pytest.mark.parametrize("mode", ["softmax", "exp_neg"])
 def test_gat_forward_parity(K, heads, D, mode):
     rng = np.random.default_rng(heads * 100 + D)
@@ -290,6 +290,28 @@ def test_gat_forward_parity(K, heads, D, mode):
         ref = oracle.gat_forward(rp, col, wh, el, er, heads, 0.2, mode=mode, elu=elu)
         out = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, elu=elu)
         assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+
+
+@pytest.mark.parametrize("heads,D", [(4, 64), (1, 256), (4, 128), (2, 48)])
+def test_gat_whole_row_kernel_matches_oracle(K, heads, D, monkeypatch):
+    """DGLLB_GAT_KERNEL=row pins the one-warp-per-row (all heads) forward kernel."""
+    monkeypatch.setenv("DGLLB_GAT_KERNEL", "row")
+    rng = np.random.default_rng(heads * 7 + D)
+    n = 500
+    rp, col = rand_csr(rng, n, n, 45, heavy=[(7, 600)])
+    wh = rng.standard_normal((n, heads * D)).astype(np.float32)
+    el = rng.standard_normal((n, heads)).astype(np.float32)
+    er = rng.standard_normal((n, heads)).astype(np.float32)
+    for mode in ("softmax", "exp_neg"):
+        ref = oracle.gat_forward(rp, col, wh, el, er, heads, 0.2, mode=mode, elu=True)
+        out, rmax, rsum = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, elu=True,
+                                        save_stats=True)
+        assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+        monkeypatch.setenv("DGLLB_GAT_KERNEL", "group")
+        out2, rmax2, rsum2 = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode,
+                                           elu=True, save_stats=True)
+        monkeypatch.setenv("DGLLB_GAT_KERNEL", "row")
+        assert torch.equal(rmax, rmax2) and rel_err(rsum.cpu().numpy(), rsum2.cpu().numpy()) <= FP32_TOL
 
 
 @pytest.mark.parametrize("heads,D", [(4, 64), (1, 47), (2, 8)])
