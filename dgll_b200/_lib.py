@@ -41,7 +41,7 @@ SIGNATURES = {
     "dgllb_ipc_import": (_I, [_P, _L, POINTER(c_void_p)]),
     "dgllb_ipc_release": (_I, [_P, _L]),
     "dgllb_gemm_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _P, _I, _I, _I, _P]),
-    "dgllb_gat_forward": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _L, _L, _I, _I, c_float, _I, _I, _P]),
+    "dgllb_gat_forward": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _L, _L, _I, _I, c_float, _I, _I, _P, _P]),
     "dgllb_gat_backward": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _L,
                                 _P, _P, _L, _P, _L, _L, _I, _I, c_float, _I, _P]),
     "dgllb_binarize_pack": (_I, [_P, _L, _P, _L, _L, _I, _P]),

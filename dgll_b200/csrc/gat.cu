@@ -43,6 +43,11 @@ struct GatParams {
     float slope;
     float sign;  // +1 softmax(lrelu), -1 exp(-lrelu)/sum
     int epi;
+    // nnz-split of long rows (whole-row kernel only): partial (acc, m, l) per (row, chunk) item in `ws`
+    int chunk;            // 0 = no split
+    const int2* items;
+    long long n_items;
+    float* ws;            // [n_items, heads*D + 8]: acc, then m[h] at +FD+h and l[h] at +FD+heads+h
 };
 
 __device__ __forceinline__ long long gat_rp(const void* p, int is64, long long i) {
@@ -193,16 +198,33 @@ gat_forward_kernel(const GatParams p) {
 // back the weight of ITS head with a broadcast LDS.  Column ids / er values of the next chunks are prefetched.
 constexpr int kRowWarps = 8;
 
-template <int NV>
+// HEAVY = false: warp w owns row w (rows longer than p.chunk edges are skipped when a plan is given).
+// HEAVY = true : warp w owns plan item w = (row, k): edges [k*chunk, (k+1)*chunk) of a long row; it writes its partial
+//                online-softmax state (unnormalised acc, running max m, running sum l) to p.ws and
+//                gat_combine_heavy_kernel merges the chunks of a row (exact log-sum-exp merge, no atomics).
+template <int NV, bool HEAVY>
 __global__ void __launch_bounds__(kRowWarps * 32)
 gat_forward_row_kernel(const GatParams p) {
     __shared__ int s_c[kRowWarps][32];
     __shared__ float s_p[kRowWarps][32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long row = static_cast<long long>(blockIdx.x) * kRowWarps + warp;
-    if (row >= p.n_dst) return;
+    const long long wid = static_cast<long long>(blockIdx.x) * kRowWarps + warp;
     const int H = p.heads, FD = p.heads * p.D;
-    const long long beg = gat_rp(p.row_ptr, p.rp64, row), end = gat_rp(p.row_ptr, p.rp64, row + 1);
+    long long row, beg, end;
+    if (HEAVY) {
+        if (wid >= p.n_items) return;
+        const int2 it = p.items[wid];
+        row = it.x;
+        const long long rb = gat_rp(p.row_ptr, p.rp64, row), re = gat_rp(p.row_ptr, p.rp64, row + 1);
+        beg = rb + static_cast<long long>(it.y) * p.chunk;
+        end = min(re, beg + p.chunk);
+    } else {
+        row = wid;
+        if (row >= p.n_dst) return;
+        beg = gat_rp(p.row_ptr, p.rp64, row);
+        end = gat_rp(p.row_ptr, p.rp64, row + 1);
+        if (p.chunk > 0 && end - beg > p.chunk) return;  // done by the heavy items
+    }
 
     // this lane's vectors and the head each one belongs to
     int hsel[NV];
@@ -308,6 +330,23 @@ gat_forward_row_kernel(const GatParams p) {
         c_nxt = c_nxt2;
     }
 
+    if (HEAVY) {
+        float* w = p.ws + wid * (FD + 8);  // row of FD floats + (m, l) per head, padded to keep 16-byte alignment
+        if (lane < H) {
+            float mm = m[0], ll = l[0];
+#pragma unroll
+            for (int h = 1; h < 4; ++h)
+                if (lane == h) { mm = m[h]; ll = l[h]; }
+            w[FD + lane] = mm;
+            w[FD + H + lane] = ll;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (von[i])
+                *reinterpret_cast<float4*>(w + (i * 32 + lane) * 4) =
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        return;
+    }
     if (lane < H) {
         float mm = m[0], ll = l[0];
 #pragma unroll
@@ -330,6 +369,48 @@ gat_forward_row_kernel(const GatParams p) {
             v[a] = t;
         }
         stg_cs_f4(p.out + row * p.ldo + (i * 32 + lane) * 4, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+// merge the chunk partials of every heavy row: warp = the k == 0 item of a row; its chunks are items [w, w + nc)
+__global__ void __launch_bounds__(256)
+gat_combine_heavy_kernel(const GatParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= p.n_items) return;
+    const int2 it = p.items[wid];
+    if (it.y != 0) return;
+    const long long row = it.x;
+    const int H = p.heads, FD = p.heads * p.D, W = FD + 8;
+    const long long deg = gat_rp(p.row_ptr, p.rp64, row + 1) - gat_rp(p.row_ptr, p.rp64, row);
+    const int nc = static_cast<int>((deg + p.chunk - 1) / p.chunk);
+    const float* base = p.ws + wid * W;
+    for (int c0 = lane * 4; c0 < FD; c0 += 128) {
+        const int h = c0 / p.D;
+        float M = -INFINITY;
+        for (int c = 0; c < nc; ++c) M = fmaxf(M, base[static_cast<long long>(c) * W + FD + h]);
+        float L = 0.f;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < nc; ++c) {
+            const float* wc = base + static_cast<long long>(c) * W;
+            const float mc = wc[FD + h];
+            const float sc = mc == -INFINITY ? 0.f : expf(mc - M);
+            L += wc[FD + H + h] * sc;
+            const float4 v = *reinterpret_cast<const float4*>(wc + c0);
+            a.x = fmaf(v.x, sc, a.x); a.y = fmaf(v.y, sc, a.y); a.z = fmaf(v.z, sc, a.z); a.w = fmaf(v.w, sc, a.w);
+        }
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+        float v[4] = {a.x * inv, a.y * inv, a.z * inv, a.w * inv};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (p.epi & DGLLB_EPI_RELU) v[k] = fmaxf(v[k], 0.f);
+            if (p.epi & DGLLB_EPI_ELU) v[k] = v[k] > 0.f ? v[k] : expm1f(v[k]);
+        }
+        *reinterpret_cast<float4*>(p.out + row * p.ldo + c0) = make_float4(v[0], v[1], v[2], v[3]);
+        if ((c0 % p.D) == 0) {  // first vector of head h records the row statistics
+            if (p.row_max) p.row_max[row * H + h] = M;
+            if (p.row_sum) p.row_sum[row * H + h] = L;
+        }
     }
 }
 
@@ -570,20 +651,48 @@ static int launch_gat_bwd(const GatBwdParams& p, cudaStream_t st) {
 }
 
 template <int VE>
-static int launch_gat_fwd(GatParams& p, cudaStream_t st) {
-    // whole-row kernel: all heads of a row in one warp (vector path, <= 4 heads, 64 < heads*D <= 512).  Measured on
-    // the products-shaped graph (4 x 64): 48.6 ms against 42.5 ms for the per-(row, head) kernel below — 4x fewer
-    // instructions do not help a latency-bound loop — so it only runs when pinned with DGLLB_GAT_KERNEL=row.
+static int launch_gat_fwd(GatParams& p, const dgllb_csr_plan* plan, cudaStream_t st) {
+    // whole-row kernel: all heads of a row in one warp (vector path, <= 4 heads, 64 < heads*D <= 512).  On a uniform
+    // degree-50 graph it runs at the SpMM rate (20.5 ms vs 19.2 ms, products-sized); on skewed graphs it needs the
+    // nnz-split plan for long rows (a 89K-edge row would otherwise be one warp's job).  DGLLB_GAT_KERNEL=group|row pins.
     const int FD = p.heads * p.D;
     const char* force = getenv("DGLLB_GAT_KERNEL");
-    if (VE == 4 && p.heads <= 4 && FD > 64 && FD <= 512 && force && force[0] == 'r') {
+    const bool row_ok = VE == 4 && p.heads <= 4 && FD > 64 && FD <= 512;
+    if (row_ok && !(force && force[0] == 'g')) {
+        const bool heavy = plan && plan->n_heavy_rows > 0;
+        float* ws = nullptr;
+        p.chunk = heavy ? plan->chunk_edges : 0;
+        p.items = heavy ? plan->items : nullptr;
+        p.n_items = heavy ? plan->n_items : 0;
+        if (heavy) {
+            DevInfo di_;
+            int rc_ = get_devinfo(&di_);
+            if (rc_ != DGLLB_OK) return rc_;
+            DGLLB_CUDA_TRY(cudaMallocAsync(&ws, sizeof(float) * static_cast<size_t>(p.n_items) * (FD + 8), st));
+        }
+        p.ws = ws;
         const long long blocks = (p.n_dst + kRowWarps - 1) / kRowWarps;
-        DGLLB_REQUIRE(blocks < (1ll << 31), "gat_forward: grid too large");
-        const unsigned g = static_cast<unsigned>(blocks);
-        if (FD <= 128) gat_forward_row_kernel<1><<<g, kRowWarps * 32, 0, st>>>(p);
-        else if (FD <= 256) gat_forward_row_kernel<2><<<g, kRowWarps * 32, 0, st>>>(p);
-        else gat_forward_row_kernel<4><<<g, kRowWarps * 32, 0, st>>>(p);
+        const long long hblocks = (p.n_items + kRowWarps - 1) / kRowWarps;
+        DGLLB_REQUIRE(blocks < (1ll << 31) && hblocks < (1ll << 31), "gat_forward: grid too large");
+        const unsigned g = static_cast<unsigned>(blocks), hg = static_cast<unsigned>(hblocks);
+#define DGLLB_GAT_ROW(NVV)                                                                        \
+        do {                                                                                      \
+            if (heavy) gat_forward_row_kernel<NVV, true><<<hg, kRowWarps * 32, 0, st>>>(p);       \
+            gat_forward_row_kernel<NVV, false><<<g, kRowWarps * 32, 0, st>>>(p);                  \
+        } while (0)
+        if (FD <= 128) DGLLB_GAT_ROW(1);
+        else if (FD <= 256) DGLLB_GAT_ROW(2);
+        else DGLLB_GAT_ROW(4);
+#undef DGLLB_GAT_ROW
+        g_launch_count.fetch_add(heavy ? 1 : 0);
         DGLLB_LAUNCH_CHECK();
+        if (heavy) {
+            gat_combine_heavy_kernel<<<static_cast<unsigned>((p.n_items * 32 + 255) / 256), 256, 0, st>>>(p);
+            g_launch_count.fetch_add(1);
+            cudaError_t e = cudaGetLastError();
+            cudaFreeAsync(ws, st);
+            if (e != cudaSuccess) { set_error("gat_forward: %s", cudaGetErrorString(e)); return DGLLB_ERR_CUDA; }
+        }
         return DGLLB_OK;
     }
     int lanes = 32;
@@ -610,8 +719,9 @@ extern "C" int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const in
                                  const float* Wh, int64_t ldw, const float* el, const float* er,
                                  int64_t ld_e, float* out, int64_t ldo, float* row_max, float* row_sum,
                                  int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                                 int mode, int epilogue, void* stream) {
+                                 int mode, int epilogue, const dgllb_csr_plan* plan, void* stream) {
     DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && heads >= 1 && D >= 1, "gat_forward: bad sizes");
+    DGLLB_REQUIRE(!plan || plan->n_rows == n_dst, "gat_forward: plan was built for another row count");
     if (n_dst == 0) return DGLLB_OK;
     DGLLB_REQUIRE(row_ptr && Wh && el && er && out, "gat_forward: null pointer");
     DGLLB_REQUIRE(ldw >= static_cast<int64_t>(heads) * D && ldo >= static_cast<int64_t>(heads) * D,
@@ -624,9 +734,10 @@ extern "C" int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const in
     p.n_dst = n_dst; p.heads = heads; p.D = D; p.n_slabs = 1; p.slope = slope;
     p.sign = mode == DGLLB_GAT_SOFTMAX ? 1.f : -1.f;
     p.epi = epilogue;
+    p.chunk = 0; p.items = nullptr; p.n_items = 0; p.ws = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = aligned16(Wh) && aligned16(out) && ldw % 4 == 0 && ldo % 4 == 0 && D % 4 == 0;
-    return vec ? launch_gat_fwd<4>(p, st) : launch_gat_fwd<1>(p, st);
+    return vec ? launch_gat_fwd<4>(p, plan, st) : launch_gat_fwd<1>(p, plan, st);
 }
 
 extern "C" int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,

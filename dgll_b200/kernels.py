@@ -278,7 +278,7 @@ def gemm(a, b, bias=None, relu=False, elu=False, trans_a=False, trans_b=False, o
 
 
 def gat_forward(row_ptr, col_idx, wh, el, er, heads, slope, mode="softmax", elu=False, save_stats=False,
-                n_dst=None, out=None):
+                n_dst=None, out=None, plan=None):
     """Fused multi-head GAT aggregation; ``wh`` is [n_src, heads*D], ``el``/``er`` are [n, heads]."""
     _need_cuda(row_ptr, col_idx, wh, el, er, out)
     rp, is64 = _rowptr(row_ptr)
@@ -303,7 +303,8 @@ def gat_forward(row_ptr, col_idx, wh, el, er, heads, slope, mode="softmax", elu=
     md = {"softmax": GAT_SOFTMAX, "exp_neg": GAT_EXP_NEG}[mode]
     check(lib().dgllb_gat_forward(_p(rp), is64, _p(col), _p(wh), ldw, _p(el), _p(er), lde, _p(out), ldo,
                                   _p(rmax), _p(rsum), n_dst, wh.size(0), heads, FD // heads, float(slope), md,
-                                  EPI_ELU if elu else 0, _stream()), "gat_forward")
+                                  EPI_ELU if elu else 0, plan._h if plan is not None else None, _stream()),
+          "gat_forward")
     return (out, rmax, rsum) if save_stats else out
 
 

@@ -284,7 +284,7 @@ class _GatFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wh, el, er, graph, heads, slope, mode):
         out, rmax, rsum = K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode,
-                                        save_stats=True, n_dst=graph.n_dst)
+                                        save_stats=True, n_dst=graph.n_dst, plan=graph.bin_plan())
         ctx.graph, ctx.heads, ctx.slope, ctx.mode = graph, heads, slope, mode
         ctx.save_for_backward(wh, el, er, out, rmax, rsum)
         return out
@@ -305,7 +305,8 @@ def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False
     if torch.is_grad_enabled() and (wh.requires_grad or el.requires_grad or er.requires_grad):
         out = _GatFn.apply(wh, el, er, graph, heads, slope, mode)
         return torch.nn.functional.elu(out) if elu else out
-    return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst)
+    return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst,
+                         plan=graph.bin_plan())
 
 
 # -------------------------------------------------------------- binarized ---

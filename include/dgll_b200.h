@@ -243,7 +243,10 @@ int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const int32_t* col_
                       const float* Wh, int64_t ldw, const float* el, const float* er,
                       int64_t ld_e, float* out, int64_t ldo, float* row_max, float* row_sum,
                       int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                      int mode, int epilogue, void* stream);
+                      int mode, int epilogue,
+                      const dgllb_csr_plan* plan /* optional: long rows are split into chunks whose partial softmax
+                                                    states are merged exactly (no atomics) */,
+                      void* stream);
 
 /*
  * Backward of dgllb_gat_forward (epilogue gradient already applied by the caller):

@@ -312,6 +312,13 @@ def test_gat_whole_row_kernel_matches_oracle(K, heads, D, monkeypatch):
                                            elu=True, save_stats=True)
         monkeypatch.setenv("DGLLB_GAT_KERNEL", "row")
         assert torch.equal(rmax, rmax2) and rel_err(rsum.cpu().numpy(), rsum2.cpu().numpy()) <= FP32_TOL
+        # long rows split into chunks, partial softmax states merged
+        plan = K.CsrPlan(dev(rp), chunk_edges=100)
+        assert plan.n_heavy_rows >= 1
+        out3, rmax3, rsum3 = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode,
+                                           elu=True, save_stats=True, plan=plan)
+        assert rel_err(out3.cpu().numpy(), ref) <= FP32_TOL
+        assert torch.equal(rmax3, rmax2) and rel_err(rsum3.cpu().numpy(), rsum2.cpu().numpy()) <= FP32_TOL
 
 
 @pytest.mark.parametrize("heads,D", [(4, 64), (1, 47), (2, 8)])

@@ -167,8 +167,15 @@ def main():
         out = torch.empty_like(wh)
         nnz = col.numel()
         nbytes = nnz * (4 + heads * D * 4 + heads * 4) + Np * (heads * D * 4 + heads * 4 + 8)
-        ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out), args.iters)
-        report("gat_forward (fused SDDMM+softmax+SpMM)", "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes)
+        gplan = K.CsrPlan(rp, chunk_edges=1024)
+        for fam in ("group", "row"):
+            os.environ["DGLLB_GAT_KERNEL"] = fam
+            ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out), args.iters)
+            report("gat_forward[%s] (fused SDDMM+softmax+SpMM)" % fam, "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes)
+        os.environ.pop("DGLLB_GAT_KERNEL", None)
+        ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out, plan=gplan), args.iters)
+        report("gat_forward[row + plan 1024]", "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes,
+               {"heavy_rows": gplan.n_heavy_rows, "chunks": gplan.n_chunks})
         ms = timeit(lambda: K.spmm_csr(rp, col, wh, reduce="sum", out=out), args.iters)
         report("spmm_full_graph (same graph, F=256)", "products-shaped", ms, nnz * (4 + 256 * 4) + Np * (256 * 4 + 8))
 
