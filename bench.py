@@ -36,6 +36,25 @@ BATCH, FANOUTS = 1024, (25, 10)
 N_BATCHES = 16  # distinct pre-sampled mini-batches cycled through the timed steps
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu summary
+    (profiles/r01_spmm_headline.txt, one `--set full` capture of the same command).  None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_spmm_headline.txt")
+    try:
+        rd = wr = None
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] == "dram__bytes_read.sum" and rd is None:
+                rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+            if len(f) >= 3 and f[0] == "dram__bytes_write.sum" and wr is None:
+                wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+            if rd is not None and wr is not None:
+                return rd + wr
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -272,6 +291,9 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    prof = os.environ.get("BENCH_PROFILE") == "1"   # ncu --profile-from-start off: capture the timed steps only
+    if prof:
+        torch.cuda.profiler.start()
     e0.record()
     total_bytes = 0
     for s in range(args.steps):
@@ -280,6 +302,8 @@ def main():
         total_bytes += bt["bytes"]
     e1.record()
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - l0
     ms = e0.elapsed_time(e1)
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
@@ -413,7 +437,8 @@ def main():
                    "setup_s": round(setup_s, 1)},
         "roofline": {"bound": "hbm", "kernel": "spmm_rowslab_kernel<float,4,32> (layer-0 mean aggregation, F=602)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                     "traffic": ncu_traffic(), "traffic_source": "profiles/r01_spmm_headline.txt (ncu --set full)",
+                     "peak_source": peak_src, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": k_bytes},
         "e2e": {"value": e2e_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": e2e_ms / args.steps},
