@@ -5,7 +5,8 @@ from .conv import (GAT, GCN, GIN, GinConv, GraphConvolution, GraphSage, Neighbor
 from .pooling import Pooling, maxPooling, meanPooling, sumPooling
 from .block_conv import GraphConv, SAGEConv
 from .models import BlockGCN, GraphSAGE
+from .ppi import GCNLayer, PPIGCN, create_sparse_adj
 
 __all__ = ["gcnConv", "GraphConvolution", "GCN", "sageConv", "NeighborAggregator", "GraphSage", "gatConv",
            "sparseGatConv", "SpecialSpmm", "SpecialSpmmFunction", "GAT", "SpGAT", "GinConv", "GIN", "sumPooling",
-           "meanPooling", "maxPooling", "Pooling", "GraphConv", "SAGEConv", "BlockGCN", "GraphSAGE"]
+           "meanPooling", "maxPooling", "Pooling", "GraphConv", "SAGEConv", "BlockGCN", "GraphSAGE", "GCNLayer", "PPIGCN", "create_sparse_adj"]

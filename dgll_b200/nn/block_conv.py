@@ -125,23 +125,24 @@ class SAGEConv(F.nn.Module):
                 feat_src = self.feat_drop(feat)
                 feat_dst = feat_src[:n_dst]
         lin_before_mp = self._in_src_feats > self._out_feats and feat_table is None
-        wn = self.fc_neigh.weight.t()
+        wn = self.fc_neigh.weight            # [out, in]: used with trans_w=True, no transpose copy
         if self._aggre_type == "mean":
             if lin_before_mp:
-                h_neigh = ops.spmm(g, ops.linear(feat_src, wn), reduce="mean")
+                h_neigh = ops.spmm(g, ops.linear(feat_src, wn, trans_w=True), reduce="mean")
             else:
-                h_neigh = ops.linear(ops.spmm(g, feat_src, reduce="mean", F=self._in_src_feats), wn)
+                h_neigh = ops.linear(ops.spmm(g, feat_src, reduce="mean", F=self._in_src_feats), wn, trans_w=True)
         elif self._aggre_type == "gcn":
             s = ops.spmm(g, feat_src, reduce="sum", F=self._in_src_feats)
-            h_neigh = ops.linear((s + feat_dst[:, :self._in_src_feats]) / (g.degrees()[:, None] + 1), wn)
+            h_neigh = ops.linear((s + feat_dst[:, :self._in_src_feats]) / (g.degrees()[:, None] + 1), wn, trans_w=True)
         else:  # pool
-            pooled = ops.linear(feat_src, self.fc_pool.weight.t(), bias=self.fc_pool.bias, relu=True)
-            h_neigh = ops.linear(ops.spmm(g, pooled, reduce="max"), wn)
+            pooled = ops.linear(feat_src, self.fc_pool.weight, trans_w=True, bias=self.fc_pool.bias, relu=True)
+            h_neigh = ops.linear(ops.spmm(g, pooled, reduce="max"), wn, trans_w=True)
         if self._aggre_type == "gcn":
             rst = h_neigh
         else:
-            rst = ops.linear(feat_dst[:, :self._in_dst_feats], self.fc_self.weight.t()) + h_neigh
-        if self.bias is not None:
+            rst = ops.linear(feat_dst[:, :self._in_dst_feats], self.fc_self.weight, trans_w=True,
+                             bias=self.bias) + h_neigh
+        if self.bias is not None and self._aggre_type == "gcn":
             rst = rst + self.bias
         if self.activation is not None:
             rst = self.activation(rst)

@@ -355,7 +355,7 @@ class GinConv(F.nn.Module):
         g = Adj if isinstance(Adj, ops.CsrGraph) else _batched_block_diag(Adj)
         flat = Feat.reshape(B * N, Fd)
         agg = ops.spmm(g, flat) + flat
-        X = ops.linear(agg, self.linear.weight.t(), bias=self.linear.bias, relu=True)
+        X = ops.linear(agg, self.linear.weight, trans_w=True, bias=self.linear.bias, relu=True)
         return X.reshape(B, N, Fd)
 
 
@@ -372,10 +372,10 @@ class GIN(F.nn.Module):
 
     def forward(self, A, X):
         g = _batched_block_diag(A)
-        X = ops.linear(X, self.in_proj.weight.t(), bias=self.in_proj.bias)
+        X = ops.linear(X, self.in_proj.weight, trans_w=True, bias=self.in_proj.bias)
         hidden_states = [X]
         for layer in self.convs:
             X = layer(g, X)
             hidden_states.append(X)
         X = torch.cat(hidden_states, dim=2).sum(dim=1)
-        return ops.linear(X, self.out_proj.weight.t(), bias=self.out_proj.bias)
+        return ops.linear(X, self.out_proj.weight, trans_w=True, bias=self.out_proj.bias)

@@ -243,9 +243,9 @@ def spmm(adj, x, values=None, reduce="sum", bias=None, relu=False, F=None):
 # ----------------------------------------------------------------- linear ---
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, relu, precision):
-        out = K.gemm(x, w, bias=bias, relu=relu, precision=precision)
-        ctx.relu, ctx.precision = relu, precision
+    def forward(ctx, x, w, bias, relu, precision, trans_w):
+        out = K.gemm(x, w, bias=bias, relu=relu, trans_b=trans_w, precision=precision)
+        ctx.relu, ctx.precision, ctx.trans_w = relu, precision, trans_w
         ctx.save_for_backward(x, w, out if relu else None)
         return out
 
@@ -257,21 +257,25 @@ class _LinearFn(torch.autograd.Function):
             g = g * (out > 0)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = K.gemm(g, w, trans_b=True, precision=ctx.precision)      # dX = G W^T
+            gx = K.gemm(g, w, trans_b=not ctx.trans_w, precision=ctx.precision)      # dX = G W^T
         if ctx.needs_input_grad[1]:
-            gw = K.gemm(x, g, trans_a=True, precision=ctx.precision)      # dW = X^T G
+            if ctx.trans_w:
+                gw = K.gemm(g, x, trans_a=True, precision=ctx.precision)              # dW[N,K] = G^T X
+            else:
+                gw = K.gemm(x, g, trans_a=True, precision=ctx.precision)              # dW[K,N] = X^T G
         if ctx.needs_input_grad[2]:
             gb = g.sum(0)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def linear(x, w, bias=None, relu=False, precision=None):
-    """x[M,K] @ w[K,N] (+ bias)(relu) on the device GEMM (fp32 exact or tcgen05 bf16)."""
+def linear(x, w, bias=None, relu=False, precision=None, trans_w=False):
+    """x[M,K] @ w[K,N] (+ bias)(relu) on the device GEMM (fp32 exact or tcgen05 bf16).  ``trans_w=True`` takes ``w``
+    stored [N,K] (an ``nn.Linear`` weight) without materialising its transpose."""
     lead = None
     if x.dim() > 2:
         lead = x.shape[:-1]
         x = x.reshape(-1, x.size(-1))
-    out = _LinearFn.apply(x, w, bias, relu, precision or _PRECISION["gemm"])
+    out = _LinearFn.apply(x, w, bias, relu, precision or _PRECISION["gemm"], trans_w)
     return out if lead is None else out.reshape(*lead, out.size(-1))
 
 

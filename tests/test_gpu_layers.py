@@ -101,6 +101,25 @@ def test_ppi_gcn_config1_forward_loss_grads(nn, gi):
     assert rel_err(b_out.grad.cpu(), g["g_b_out"]) <= GRAD_TOL
 
 
+def test_ppi_model_class_drop_in(nn):
+    """The Evaluation/PPI GCN class itself (same state-dict keys) on the golden graph: logits, loss, one Adam step."""
+    g = golden("ppi_gcn_g8")
+    model = nn.PPIGCN(50, 64, 121, 2).cuda()
+    assert sorted(model.state_dict()) == ["layers.0.weight", "layers.1.weight", "out_layer.bias", "out_layer.weight"]
+    model.load_state_dict({"layers.0.weight": cu(g["w0"]), "layers.1.weight": cu(g["w1"]),
+                           "out_layer.weight": cu(g["w_out"]), "out_layer.bias": cu(g["b_out"])})
+    ei, x, y = cu(g["edge_index"], torch.int64), cu(g["feats"]), cu(g["labels"])
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    out = model(ei, x)
+    loss = torch.nn.CrossEntropyLoss()(out, y)
+    assert rel_err(out.detach().cpu(), g["logits"]) <= OUT_TOL
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    opt.zero_grad(); loss.backward(); opt.step()
+    assert rel_err(model.layers[0].weight.grad.cpu(), g["g_w0"]) <= GRAD_TOL
+    out2 = model(ei, x)                        # second call reuses the cached CSR of this edge_index tensor
+    assert torch.isfinite(out2).all() and hasattr(ei, "_dgllb_csr")
+
+
 # ----------------------------------------------------------------- GAT -----
 def _load_gat(model, g, heads):
     with torch.no_grad():
