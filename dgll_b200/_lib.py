@@ -47,6 +47,7 @@ SIGNATURES = {
     "dgllb_binarize_pack": (_I, [_P, _L, _P, _L, _L, _I, _P]),
     "dgllb_bin_spmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
     "dgllb_sample_neighbors": (_I, [_P, _I, _P, _P, _I, _L, _I, c_uint64, _P, _P, _P]),
+    "dgllb_build_block": (_I, [_P, _L, _P, _P, _L, _P, _P, _P, _P]),
     "launch_gcn_fused_kernel": (None, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "launch_gcn_fused_kernel_backward_optimized": (None, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "dgllb_gcn_fused_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

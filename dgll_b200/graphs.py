@@ -165,17 +165,24 @@ def compact_dst_first(dst_ids, nbr_global):
     return uniq[order], local[dst_ids.numel():].to(torch.int32)
 
 
-def sample_blocks(row_ptr, col_idx, seeds, fanouts, rng_seed=0):
+def sample_blocks(row_ptr, col_idx, seeds, fanouts, rng_seed=0, builder="device"):
     """Device-side DGL-style neighbour sampling: ``fanouts[0]`` applies to the INPUT layer, the last entry to the
     seed/output layer (the order DGLLNeighborSampler consumes them, dgll/sampling/dgllsampler.py:14).
-    Returns blocks[0..L-1] (input layer first), each dst-first compacted."""
+    Returns blocks[0..L-1] (input layer first), each dst-first compacted.
+    ``builder='device'``: ``dgllb_build_block`` (hash-based, one read-back per layer); ``'torch'``: the sort-based
+    formulation with torch.unique (kept as the cross-check; identical output)."""
     blocks = []
     cur = seeds.to(torch.int64)
     for li, fanout in enumerate(reversed(list(fanouts))):
         b_rp, b_col = K.sample_neighbors(row_ptr, col_idx, cur, fanout, rng_seed=rng_seed * 1000003 + li)
-        nnz = int(b_rp[-1].item())
-        b_col = b_col[:nnz]
-        src_ids, col_local = compact_dst_first(cur, b_col)
+        if builder == "device":
+            src_cap, col_cap, counts = K.build_block(cur, b_rp, b_col)
+            num_src, nnz = counts.tolist()                      # the layer's only device->host read-back
+            src_ids, col_local, b_col = src_cap[:num_src], col_cap[:nnz], b_col[:nnz]
+        else:
+            nnz = int(b_rp[-1].item())
+            b_col = b_col[:nnz]
+            src_ids, col_local = compact_dst_first(cur, b_col)
         blocks.insert(0, Block(b_rp, col_local, b_col, src_ids, cur.numel()))
         cur = src_ids
     return blocks

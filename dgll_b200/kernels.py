@@ -400,6 +400,25 @@ def sample_neighbors(row_ptr, col_idx, seeds, fanout, rng_seed=0):
     return out_rp, out_col
 
 
+def build_block(dst_ids, row_ptr, nbr_global):
+    """dst-first compaction on the device.  Returns (src_ids int64[cap], col_local int32[cap_nnz], counts int32[2] on
+    the device = {num_src, nnz}); slice with the counts after reading them back once."""
+    _need_cuda(dst_ids, row_ptr, nbr_global)
+    dst_ids = dst_ids.to(torch.int64).contiguous()
+    row_ptr = row_ptr.contiguous()
+    if row_ptr.dtype != torch.int32:
+        raise TypeError("build_block: row_ptr must be int32 (output of sample_neighbors)")
+    nbr = _index32(nbr_global, "nbr_global")
+    n_dst, cap = dst_ids.numel(), nbr.numel()
+    dev = dst_ids.device
+    src_ids = torch.empty(n_dst + cap, dtype=torch.int64, device=dev)
+    col_local = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    check(lib().dgllb_build_block(_p(dst_ids), n_dst, _p(row_ptr), _p(nbr), cap, _p(src_ids), _p(col_local), _p(counts),
+                                  _stream()), "build_block")
+    return src_ids, col_local, counts
+
+
 def gcn_fused_forward_v2(row_ptr, col_idx, values, X, W, num_neighbors, actual_F):
     _need_cuda(row_ptr, col_idx, values, X, W, num_neighbors)
     N, Fp, Hd = X.size(0), X.size(1), W.size(1)

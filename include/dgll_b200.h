@@ -312,6 +312,21 @@ int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, const int32_t*
                            uint64_t rng_seed, int32_t* out_row_ptr, int32_t* out_col,
                            void* stream);
 
+/*
+ * Block (MFG) construction: dst-first compaction of a sampled edge list, on the device.
+ *   dst_ids     int64[n_dst]  (unique; they become local ids 0..n_dst-1 in order)
+ *   row_ptr     int32[n_dst+1], nbr_global int32[>= row_ptr[n_dst]]  (output of dgllb_sample_neighbors);
+ *               nnz_cap = allocated length of nbr_global / col_local (the true nnz is read on the device)
+ *   src_ids     int64[n_dst + nnz_cap] out: unique ids of cat(dst_ids, neighbours) in first-occurrence order
+ *   col_local   int32[nnz_cap] out: neighbours relabelled into src_ids' index space
+ *   counts_out  int32[2] out (device): {num_src, nnz}
+ * Deterministic (no sort, no order-dependent atomics).  Replaces the relabelling DGL's to_block does for the blocks
+ * consumed at GPU Accelerator/MQGCN.py:41-50 and the unique-node bookkeeping of dgll/sampling/base_sampler.py:81.
+ */
+int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const int32_t* row_ptr,
+                      const int32_t* nbr_global, int64_t nnz_cap, int64_t* src_ids, int32_t* col_local,
+                      int32_t* counts_out, void* stream);
+
 /* ------------------------------------------------------------ legacy ABI -- */
 
 /*

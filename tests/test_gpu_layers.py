@@ -456,3 +456,34 @@ def test_graph_cache_server_matches_reference_semantics():
     nf2 = NodeFlow([torch.from_numpy(layers[0])])
     srv2.fetch_data(nf2)
     assert np.array_equal(nf2._node_frames[0]["features"].cpu().numpy(), host["features"][nid_map[layers[0]]])
+
+
+# ------------------------------------------------------- normalisation -----
+def test_normalisation_helpers_match_reference():
+    """a17: host helpers reproduce the reference's golden ``normalize`` output; device versions equal them."""
+    import scipy.sparse as sp
+    from dgll_b200 import ops
+    from dgll_b200.nn import utils as U
+    g = golden("nn_normalize")
+    raw = sp.csr_matrix(g["raw"])
+    out = U.normalize(raw)
+    assert rel_err(np.asarray(out.todense()), g["dense"]) <= 1e-6
+    t = U.sparse_mx_to_torch_sparse_tensor(out, device="cuda").coalesce()
+    assert np.array_equal(t.indices().cpu().numpy(), g["indices"]) and rel_err(t.values().cpu().numpy(), g["values"]) <= 1e-6
+    gcsr = ops.CsrGraph.from_dense(cu(g["raw"]))
+    nz = (cu(g["raw"]) > 0).nonzero()
+    gcsr = gcsr.with_values(cu(g["raw"])[nz[:, 0], nz[:, 1]])
+    dv = U.row_normalize_csr(gcsr)
+    dense = torch.zeros(g["raw"].shape, device="cuda")
+    rows = torch.repeat_interleave(torch.arange(dv.n_dst, device="cuda"), dv.row_ptr[1:] - dv.row_ptr[:-1])
+    dense[rows, dv.col.long()] = dv.values
+    assert rel_err(dense.cpu().numpy(), g["dense"]) <= 1e-6
+    a = (np.random.default_rng(0).random((50, 50)) < 0.1).astype(np.float64)
+    a = ((a + a.T) > 0).astype(np.float64)
+    ref = L.sym_norm_adjacency(a)
+    sv = U.sym_normalize_csr(ops.CsrGraph.from_dense(cu(a)))
+    dense = torch.zeros((50, 50), device="cuda")
+    rows = torch.repeat_interleave(torch.arange(50, device="cuda"), sv.row_ptr[1:] - sv.row_ptr[:-1])
+    dense[rows, sv.col.long()] = sv.values
+    assert rel_err(dense.cpu().numpy(), ref) <= 1e-6
+    assert rel_err(np.asarray(U.normalize_lap(sp.csr_matrix(a)).todense()), ref) <= 1e-6

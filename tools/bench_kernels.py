@@ -178,6 +178,15 @@ def main():
                {"heavy_rows": gplan.n_heavy_rows, "chunks": gplan.n_chunks})
         ms = timeit(lambda: K.spmm_csr(rp, col, wh, reduce="sum", out=out), args.iters)
         report("spmm_full_graph (same graph, F=256)", "products-shaped", ms, nnz * (4 + 256 * 4) + Np * (256 * 4 + 8))
+        # backward: pass 1 over the CSR (alpha, dz per edge), pass 2 over the transposed CSR (d_Wh, d_er)
+        o2, rmax, rsum = K.gat_forward(rp, col, wh, el, er, heads, 0.2, save_stats=True, plan=gplan)
+        trp, tcol, _, perm = K.csr_transpose(rp, col, Np, want_perm=True)
+        gout = torch.randn_like(wh)
+        ms_t = timeit(lambda: K.csr_transpose(rp, col, Np, want_perm=True), 3)
+        ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2), 5)
+        # bytes: pass 1 reads Wh_j + writes 8 B/(edge, head); pass 2 reads g_i + 8 B/(edge, head) per transposed edge
+        bwd_bytes = nnz * (4 + heads * D * 4 + heads * 8) * 2 + Np * (heads * D * 4) * 3
+        report("gat_backward (2 passes, no atomics)", "products-shaped", ms, bwd_bytes, {"csr_transpose_ms_once": round(ms_t, 3)})
 
 
 if __name__ == "__main__":
