@@ -13,6 +13,8 @@ gen = torch.Generator(device=dev).manual_seed(0)
 labels = torch.randint(0, 41, (N,), device=dev, generator=gen)
 seeds = torch.randperm(int(0.66 * N), device=dev, generator=gen)[:1024 * 40]
 model = dnn.GraphSAGE(F, 256, 41, 2, torch.relu, 0.0).to(dev)
+from dgll_b200 import ops
+ops.set_gemm_precision("bf16")
 opt = torch.optim.Adam(model.parameters(), lr=0.003)
 pre = T.make_batches(rp, col, seeds, (25, 10), 1024, rng_seed=3)
 T.sage_epoch(model, opt, table, labels, F, batches=pre[:8])
@@ -21,10 +23,4 @@ pr.enable()
 r = T.sage_epoch(model, opt, table, labels, F, batches=pre)
 pr.disable()
 print(r)
-pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
-pr = cProfile.Profile()
-pr.enable()
-r = T.sage_epoch(model, opt, table, labels, F, rp, col, seeds, (25, 10), 1024)
-pr.disable()
-print(r)
-pstats.Stats(pr).sort_stats("cumulative").print_stats(30)
+pstats.Stats(pr).sort_stats("tottime").print_stats(28)
