@@ -1,0 +1,202 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle cannot run these sizes in
+seconds): exact row sums of ones, linearity, agreement between independent kernel families, checksums of checksums,
+gather round trips, structural sampler invariants.  Graphs are the synthetic shapes bench.py / tools use."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    assert torch.cuda.is_available()
+    from dgll_b200 import kernels
+    return kernels
+
+
+@pytest.fixture(scope="module")
+def reddit():
+    """configs[1]/[3]: N=232,965, nnz=114,615,892 (R-MAT, skewed: rows of up to ~100K edges)."""
+    from dgll_b200 import graphs as G
+    N, NNZ, F, _ = G.SHAPES["reddit"]
+    rp, col = G.rmat_csr(N, NNZ, seed=0, device="cuda")
+    return N, NNZ, F, rp, col
+
+
+def _with_kernel(name, fn):
+    old = os.environ.get("DGLLB_SPMM_KERNEL")
+    os.environ["DGLLB_SPMM_KERNEL"] = name
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("DGLLB_SPMM_KERNEL", None)
+        else:
+            os.environ["DGLLB_SPMM_KERNEL"] = old
+
+
+def test_full_reddit_spmm_properties(K, reddit):
+    N, NNZ, F, rp, col = reddit
+    assert int(rp[-1]) == NNZ and col.numel() == NNZ
+    deg = (rp[1:] - rp[:-1])
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Fw = 64                                   # narrow features keep the test at a few seconds; the kernels are the same
+    x = torch.randn((N, Fw), device="cuda", generator=g)
+    y = torch.randn((N, Fw), device="cuda", generator=g)
+    plan = K.CsrPlan(rp, chunk_edges=4096)
+    assert plan.n_heavy_rows == int((deg > 4096).sum())
+    # (1) mean of ones is exactly 1 on non-empty rows, 0 on empty rows — every kernel family, with and without plan
+    ones = torch.ones((N, Fw), device="cuda")
+    expect = (deg > 0).float()[:, None].expand(-1, Fw)
+    # (deg * fl(1/deg) can be 1 - 2^-24 for some degrees: one ulp of slack)
+    for fam in ("rowsplit", "stream"):
+        out = _with_kernel(fam, lambda: K.spmm_csr(rp, col, ones, reduce="mean"))
+        assert (out - expect).abs().max().item() <= 1.2e-7, fam
+        assert torch.count_nonzero(out[deg == 0]).item() == 0
+    assert (K.spmm_csr(rp, col, ones, reduce="mean", plan=plan) - expect).abs().max().item() <= 1e-6
+    # (2) sum of ones = in-degree (exact in fp32: degrees < 2^24)
+    out = K.spmm_csr(rp, col, ones, reduce="sum", plan=plan)
+    assert torch.equal(out[:, 0], deg.float())
+    # (3) the two deterministic LDG kernels add a row's edges in the same (CSR) order: bitwise equal
+    a = _with_kernel("rowsplit", lambda: K.spmm_csr(rp, col, x, reduce="sum"))
+    b = _with_kernel("stream", lambda: K.spmm_csr(rp, col, x, reduce="sum"))
+    assert torch.equal(a, b)
+    # (4) the nnz-split plan (atomics on long rows) agrees to fp32 reordering error
+    c = K.spmm_csr(rp, col, x, reduce="sum", plan=plan)
+    scale = a.abs().max().item()
+    assert (a - c).abs().max().item() <= 1e-5 * scale
+    # (5) linearity
+    lhs = K.spmm_csr(rp, col, x + y, reduce="sum")
+    rhs = a + K.spmm_csr(rp, col, y, reduce="sum")
+    assert (lhs - rhs).abs().max().item() <= 1e-5 * lhs.abs().max().item()
+    # (6) max >= mean, and max over a row of a constant column is that constant
+    mx = K.spmm_csr(rp, col, x, reduce="max")
+    mean = K.spmm_csr(rp, col, x, reduce="mean")
+    nz = deg > 0
+    assert bool((mx[nz] >= mean[nz] - 1e-4).all())
+    # (7) transpose twice = identity on the structure (checksum of checksums: per-row sums of column ids)
+    t_rp, t_col, _, perm = K.csr_transpose(rp, col, N, want_perm=True)
+    assert int(t_rp[-1]) == NNZ
+    tt_rp, tt_col, _, _ = K.csr_transpose(t_rp, t_col, N)
+    assert torch.equal(tt_rp, rp)
+    # rows of the double transpose hold the same column multiset as the original (it is stably sorted by column)
+    s1 = torch.zeros(N, dtype=torch.int64, device="cuda").index_add_(
+        0, torch.repeat_interleave(torch.arange(N, device="cuda"), deg), col.long())
+    s2 = torch.zeros(N, dtype=torch.int64, device="cuda").index_add_(
+        0, torch.repeat_interleave(torch.arange(N, device="cuda"), deg), tt_col.long())
+    assert torch.equal(s1, s2)
+
+
+def test_full_reddit_width_602_kernels_agree(K, reddit):
+    """F=602 (stride 604), the headline width: row-split, streaming and plan kernels on the full graph."""
+    from dgll_b200 import graphs as G
+    N, NNZ, F, rp, col = reddit
+    table = G.feature_table(N, F, seed=3)
+    plan = K.CsrPlan(rp, chunk_edges=4096)
+    a = _with_kernel("rowsplit", lambda: K.spmm_csr(rp, col, table, reduce="mean", F=F))
+    b = _with_kernel("stream", lambda: K.spmm_csr(rp, col, table, reduce="mean", F=F))
+    assert a.shape == (N, F) and torch.equal(a, b)
+    c = K.spmm_csr(rp, col, table, reduce="mean", F=F, plan=plan)
+    assert (a - c).abs().max().item() <= 1e-5 * a.abs().max().item()
+    # bf16 table (stride 608) within the bf16 bar of the fp32 result
+    tb = G.feature_table(N, F, seed=3, dtype=torch.bfloat16)
+    d = K.spmm_csr(rp, col, tb, reduce="mean", F=F, plan=plan)
+    assert (a - d).abs().max().item() <= 1e-2 * a.abs().max().item()
+
+
+def test_full_size_gather_round_trip(K):
+    """1,000,000 rows of 2,416 B through the TMA gather: exact copy, and gather(gather(T, p), p^-1) == T."""
+    from dgll_b200 import graphs as G
+    N, _, F, _ = G.SHAPES["reddit"]
+    table = G.feature_table(N, F, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ids = torch.randint(0, N, (1000000,), device="cuda", generator=g)
+    out = K.gather_rows(table, ids)
+    assert torch.equal(out, table[ids])
+    perm = torch.randperm(N, device="cuda", generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(N, device="cuda")
+    assert torch.equal(K.gather_rows(K.gather_rows(table, perm), inv), table)
+    assert torch.equal(K.gather_rows(table, ids.to(torch.int32)), out)
+
+
+def test_full_reddit_binarized_checksums(K, reddit):
+    """configs[3]: counts summed over features == neighbours' popcounts summed over the row (checksum of checksums);
+    plan and no-plan paths bit-identical; +-1 mean consistent with the counts."""
+    from dgll_b200 import graphs as G
+    N, NNZ, F, rp, col = reddit
+    table = G.feature_table(N, F, seed=7)
+    packed = K.binarize_pack(table[:, :F])
+    assert packed.shape == (N, 20)
+    bits = (table[:, :F] >= 0)
+    pop = bits.sum(1)                                               # popcount of every packed row (<= 602), int64
+    plan = K.CsrPlan(rp, chunk_edges=1024)
+    cnt = K.bin_spmm_csr(rp, col, packed, F, mode="count", plan=plan)
+    deg = (rp[1:] - rp[:-1])
+    rows = torch.repeat_interleave(torch.arange(N, device="cuda"), deg)
+    want = torch.zeros(N, dtype=torch.int64, device="cuda").index_add_(0, rows, pop[col.long()])
+    assert torch.equal(cnt.sum(1, dtype=torch.int64), want)         # exact integer identity (up to 3e7 per row)
+    assert int(cnt.max()) <= int(deg.max()) and int(cnt.min()) >= 0
+    # rows short enough for the unsplit kernel must agree bit for bit with the split run
+    cnt2 = K.bin_spmm_csr(rp, col, packed, F, mode="count")
+    assert torch.equal(cnt, cnt2)
+    mean = K.bin_spmm_csr(rp, col, packed, F, mode="mean", plan=plan)
+    d = deg.float()[:, None]
+    ref = torch.where(d > 0, (2 * cnt.float() - d) / d.clamp(min=1), torch.zeros_like(mean))
+    assert (mean - ref).abs().max().item() <= 1e-6
+
+
+def test_full_products_gat_properties(K):
+    """configs[2]: products-shaped graph (N=2,449,029, symmetrised nnz=123,718,280), 4 heads x 64.
+    Attention weights sum to 1: aggregating all-ones features gives exactly-1 rows (to fp32 rounding); the per-head
+    and whole-row kernels (with the long-row plan) agree; statistics are finite."""
+    from dgll_b200 import graphs as G
+    Np, E, _, _ = G.SHAPES["products"]
+    rp, col = G.rmat_csr(Np, 2 * E, seed=2, device="cuda", symmetric=True)
+    assert col.numel() == 2 * E
+    heads, D = 4, 64
+    g = torch.Generator(device="cuda").manual_seed(4)
+    el = torch.randn((Np, heads), device="cuda", generator=g)
+    er = torch.randn((Np, heads), device="cuda", generator=g)
+    ones = torch.ones((Np, heads * D), device="cuda")
+    plan = K.CsrPlan(rp, chunk_edges=1024)
+    deg = rp[1:] - rp[:-1]
+    for mode in ("softmax", "exp_neg"):
+        out, rmax, rsum = K.gat_forward(rp, col, ones, el, er, heads, 0.2, mode=mode, save_stats=True, plan=plan)
+        nz = deg > 0
+        assert (out[nz] - 1).abs().max().item() <= 1e-5
+        assert torch.count_nonzero(out[~nz]).item() == 0
+        assert bool(torch.isfinite(rmax[nz]).all()) and bool((rsum[nz] > 0).all())
+    wh = torch.randn((Np, heads * D), device="cuda", generator=g)
+    a = K.gat_forward(rp, col, wh, el, er, heads, 0.2, plan=plan)
+    os.environ["DGLLB_GAT_KERNEL"] = "group"
+    try:
+        b = K.gat_forward(rp, col, wh, el, er, heads, 0.2)
+    finally:
+        os.environ.pop("DGLLB_GAT_KERNEL", None)
+    assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1.0)
+
+
+def test_full_reddit_sampler_and_blocks(K, reddit):
+    """Fan-out 25/10 blocks of 8,192 seeds on the full graph: counts = min(deg, fanout), sampled ids are neighbours,
+    no duplicates within a row, dst-first compaction consistent."""
+    from dgll_b200 import graphs as G
+    N, NNZ, F, rp, col = reddit
+    g = torch.Generator(device="cuda").manual_seed(9)
+    seeds = torch.randperm(N, device="cuda", generator=g)[:8192]
+    b0, b1 = G.sample_blocks(rp, col, seeds, (25, 10), rng_seed=1)
+    deg = (rp[1:] - rp[:-1])
+    assert torch.equal((b1.row_ptr[1:] - b1.row_ptr[:-1]).long(), deg[seeds].clamp(max=10))
+    assert torch.equal((b0.row_ptr[1:] - b0.row_ptr[:-1]).long(), deg[b1.src_ids].clamp(max=25))
+    assert b1.src_ids[:8192].equal(seeds) and b0.num_dst == b1.num_src
+    assert torch.equal(b0.src_ids[b0.col.long()], b0.col_global.long())
+    # sampled ids are in-neighbours of their seed, without replacement (check 200 rows on the host)
+    rp_h, col_h = rp.cpu().numpy(), col.cpu().numpy()
+    brp, bcol, s = b1.row_ptr.cpu().numpy(), b1.col_global.cpu().numpy(), seeds.cpu().numpy()
+    for i in range(0, 8192, 41):
+        got = bcol[brp[i]:brp[i + 1]]
+        nb = col_h[rp_h[s[i]]:rp_h[s[i] + 1]]
+        assert len(set(got.tolist())) == len(got) and set(got.tolist()) <= set(nb.tolist())
