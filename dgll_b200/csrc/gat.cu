@@ -495,27 +495,39 @@ gat_backward_edge_kernel(const GatBwdParams p) {
             my_dact = p.sign * (z > 0.f ? 1.f : p.slope);
         }
         float my_dalpha = 0.f;
-        for (int k0 = 0; k0 < n; ++k0) {
-            const long long c = __shfl_sync(gmask, my_c, k0, LANES);
-            float part = 0.f;
+        // kGatUnroll source rows in flight per lane before any reduction (the first version loaded one row, reduced,
+        // then loaded the next: one dependent DRAM round trip per edge)
+        for (int k0 = 0; k0 < n; k0 += kGatUnroll) {
+            float part[kGatUnroll];
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-                const int dcol = (k * LANES + lig) * VE;
-                if (dcol < p.D) {
-                    const float* w = p.Wh + c * p.ldw + head * p.D + dcol;
-                    if (VE == 4) {
-                        const float4 v = ldg_nc_f4(w);
-                        part = fmaf(gi[k][0], v.x, part);
-                        part = fmaf(gi[k][1 % VE], v.y, part);
-                        part = fmaf(gi[k][2 % VE], v.z, part);
-                        part = fmaf(gi[k][3 % VE], v.w, part);
-                    } else {
-                        part = fmaf(gi[k][0], ldg_nc_f1(w), part);
+            for (int u = 0; u < kGatUnroll; ++u) {
+                const long long c = __shfl_sync(gmask, my_c, (k0 + u) & (LANES - 1), LANES);
+                float pr = 0.f;
+                if (k0 + u < n) {
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        const int dcol = (k * LANES + lig) * VE;
+                        if (dcol < p.D) {
+                            const float* w = p.Wh + c * p.ldw + head * p.D + dcol;
+                            if (VE == 4) {
+                                const float4 v = ldg_nc_f4(w);
+                                pr = fmaf(gi[k][0], v.x, pr);
+                                pr = fmaf(gi[k][1 % VE], v.y, pr);
+                                pr = fmaf(gi[k][2 % VE], v.z, pr);
+                                pr = fmaf(gi[k][3 % VE], v.w, pr);
+                            } else {
+                                pr = fmaf(gi[k][0], ldg_nc_f1(w), pr);
+                            }
+                        }
                     }
                 }
+                part[u] = pr;
             }
-            const float dot = group_sum<LANES>(part, gmask);
-            if (lig == k0) my_dalpha = dot;
+#pragma unroll
+            for (int u = 0; u < kGatUnroll; ++u) {
+                const float dot = group_sum<LANES>(part[u], gmask);
+                if (lig == k0 + u) my_dalpha = dot;
+            }
         }
         if (lig < n) {
             const float dz = my_alpha * (my_dalpha - c_i) * my_dact;
