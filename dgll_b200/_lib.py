@@ -41,9 +41,11 @@ SIGNATURES = {
     "dgllb_ipc_import": (_I, [_P, _L, POINTER(c_void_p)]),
     "dgllb_ipc_release": (_I, [_P, _L]),
     "dgllb_gemm_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _L, _L, _L, _P, _I, _I, _I, _P]),
-    "dgllb_gat_forward": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _L, _L, _I, _I, c_float, _I, _I, _P, _P]),
+    "dgllb_gat_forward": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _L, _L, _I, _I, c_float, _I, _I, c_float,
+                               c_uint64, _P, _P]),
+    "dgllb_gat_dropout_mask": (_I, [c_uint64, _L, _I, c_float, _P, _P]),
     "dgllb_gat_backward": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _L,
-                                _P, _P, _L, _P, _L, _L, _I, _I, c_float, _I, _P]),
+                                _P, _P, _L, _P, _L, _L, _I, _I, c_float, _I, c_float, c_uint64, _P]),
     "dgllb_binarize_pack": (_I, [_P, _L, _P, _L, _L, _I, _P]),
     "dgllb_bin_spmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
     "dgllb_sample_neighbors": (_I, [_P, _I, _P, _P, _I, _L, _I, c_uint64, _P, _P, _P]),

@@ -43,6 +43,10 @@ struct GatParams {
     float slope;
     float sign;  // +1 softmax(lrelu), -1 exp(-lrelu)/sum
     int epi;
+    // attention dropout (gatconv.py:37 / :132): keep iff hash(seed, edge, head) >= drop_thresh; kept weights * drop_scale
+    unsigned drop_thresh;  // 0 = no dropout
+    float drop_scale;
+    unsigned long long seed;
     // nnz-split of long rows (whole-row kernel only): partial (acc, m, l) per (row, chunk) item in `ws`
     int chunk;            // 0 = no split
     const int2* items;
@@ -66,6 +70,17 @@ __device__ __forceinline__ float group_sum(float v, unsigned gmask) {
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, LANES);
     return v;
+}
+
+// counter-based dropout mask: one decision per (edge position in the CSR, head), reproducible in the backward
+__device__ __forceinline__ float gat_keep_scale(unsigned long long seed, long long e, int h, int H, unsigned thresh,
+                                                float scale) {
+    unsigned long long z = seed + static_cast<unsigned long long>(e) * static_cast<unsigned>(H) + static_cast<unsigned>(h);
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return static_cast<unsigned>(z >> 32) >= thresh ? scale : 0.f;
 }
 
 constexpr int kGatThreads = 256;
@@ -129,8 +144,10 @@ gat_forward_kernel(const GatParams p) {
         const float mc = group_max<LANES>(my_s, gmask);
         const float m_new = fmaxf(m, mc);
         const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
-        const float my_p = (lig < n) ? expf(my_s - m_new) : 0.f;
+        float my_p = (lig < n) ? expf(my_s - m_new) : 0.f;
         l = l * corr + group_sum<LANES>(my_p, gmask);
+        // dropout acts on the normalised attention: the row sum keeps every edge, the aggregation drops some
+        if (p.drop_thresh) my_p *= gat_keep_scale(p.seed, e0 + lig, head, p.heads, p.drop_thresh, p.drop_scale);
         m = m_new;
 #pragma unroll
         for (int a = 0; a < VE; ++a) acc[a] *= corr;
@@ -283,7 +300,8 @@ gat_forward_row_kernel(const GatParams p) {
                 const float pe = (lane < n) ? expf(sc - m_new) : 0.f;
                 l[h] = l[h] * corr[h] + warp_sum(pe);
                 m[h] = m_new;
-                s_p[warp][lane][h] = pe;
+                s_p[warp][lane][h] = p.drop_thresh ? pe * gat_keep_scale(p.seed, e0 + lane, h, H, p.drop_thresh, p.drop_scale)
+                                                   : pe;
             }
         }
         s_c[warp][lane] = c_cur;
@@ -445,6 +463,9 @@ struct GatBwdParams {
     int D;
     float slope;
     float sign;
+    unsigned drop_thresh;  // same mask as the forward (seed, edge position, head)
+    float drop_scale;
+    unsigned long long seed;
 };
 
 // Pass 1: group = (dst row i, head).  Lane columns: chunk k covers (k*LANES + lig)*VE.
@@ -530,8 +551,12 @@ gat_backward_edge_kernel(const GatBwdParams p) {
             }
         }
         if (lig < n) {
-            const float dz = my_alpha * (my_dalpha - c_i) * my_dact;
-            p.ws[(e0 + lig) * p.heads + head] = make_float2(my_alpha, dz);
+            // with dropout the aggregation weight is alpha * m' (m' = mask / (1-p)); c_i = <g_i, out_i> already
+            // contains the same m' through the forward output
+            const float mk = p.drop_thresh ? gat_keep_scale(p.seed, e0 + lig, head, p.heads, p.drop_thresh, p.drop_scale)
+                                           : 1.f;
+            const float dz = my_alpha * (mk * my_dalpha - c_i) * my_dact;
+            p.ws[(e0 + lig) * p.heads + head] = make_float2(my_alpha * mk, dz);
             del_acc += dz;
         }
     }
@@ -723,15 +748,38 @@ static int launch_gat_fwd(GatParams& p, const dgllb_csr_plan* plan, cudaStream_t
     return DGLLB_OK;
 }
 
+__global__ void gat_dropout_mask_kernel(unsigned long long seed, long long nnz, int H, unsigned thresh, float scale,
+                                        float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nnz * H) return;
+    out[i] = gat_keep_scale(seed, i / H, static_cast<int>(i % H), H, thresh, scale);
+}
+
 }  // namespace dgllb
 
 using namespace dgllb;
+
+extern "C" int dgllb_gat_dropout_mask(uint64_t drop_seed, int64_t nnz, int heads, float drop_p, float* mask_out,
+                                      void* stream) {
+    DGLLB_REQUIRE(nnz >= 0 && heads >= 1 && drop_p >= 0.f && drop_p < 1.f && (nnz == 0 || mask_out),
+                  "gat_dropout_mask: bad arguments");
+    if (nnz == 0) return DGLLB_OK;
+    unsigned th = drop_p > 0.f ? static_cast<unsigned>(static_cast<double>(drop_p) * 4294967296.0) : 0u;
+    if (drop_p > 0.f && th == 0u) th = 1u;
+    const long long total = nnz * heads;
+    gat_dropout_mask_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        drop_seed, nnz, heads, th, 1.f / (1.f - drop_p), mask_out);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
 
 extern "C" int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
                                  const float* Wh, int64_t ldw, const float* el, const float* er,
                                  int64_t ld_e, float* out, int64_t ldo, float* row_max, float* row_sum,
                                  int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                                 int mode, int epilogue, const dgllb_csr_plan* plan, void* stream) {
+                                 int mode, int epilogue, float drop_p, uint64_t drop_seed,
+                                 const dgllb_csr_plan* plan, void* stream) {
+    DGLLB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gat_forward: dropout probability must be in [0, 1)");
     DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && heads >= 1 && D >= 1, "gat_forward: bad sizes");
     DGLLB_REQUIRE(!plan || plan->n_rows == n_dst, "gat_forward: plan was built for another row count");
     if (n_dst == 0) return DGLLB_OK;
@@ -746,6 +794,10 @@ extern "C" int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const in
     p.n_dst = n_dst; p.heads = heads; p.D = D; p.n_slabs = 1; p.slope = slope;
     p.sign = mode == DGLLB_GAT_SOFTMAX ? 1.f : -1.f;
     p.epi = epilogue;
+    p.drop_thresh = drop_p > 0.f ? static_cast<unsigned>(static_cast<double>(drop_p) * 4294967296.0) : 0u;
+    if (drop_p > 0.f && p.drop_thresh == 0u) p.drop_thresh = 1u;
+    p.drop_scale = 1.f / (1.f - drop_p);
+    p.seed = drop_seed;
     p.chunk = 0; p.items = nullptr; p.n_items = 0; p.ws = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = aligned16(Wh) && aligned16(out) && ldw % 4 == 0 && ldo % 4 == 0 && D % 4 == 0;
@@ -759,7 +811,8 @@ extern "C" int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const i
                                   const float* row_sum, const float* g, int64_t ldg, float* d_Wh,
                                   int64_t ldd, float* d_el, float* d_er, int64_t ld_de, float* edge_ws,
                                   int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                                  int mode, void* stream) {
+                                  int mode, float drop_p, uint64_t drop_seed, void* stream) {
+    DGLLB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gat_backward: dropout probability must be in [0, 1)");
     DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && heads >= 1 && D >= 1, "gat_backward: bad sizes");
     if (n_dst == 0 && n_src == 0) return DGLLB_OK;
     DGLLB_REQUIRE(row_ptr && t_row_ptr && Wh && el && er && out && row_max && row_sum && g && d_Wh && d_el &&
@@ -776,6 +829,10 @@ extern "C" int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const i
     p.d_el = d_el; p.d_er = d_er; p.ld_de = ld_de; p.ws = reinterpret_cast<float2*>(edge_ws);
     p.n_dst = n_dst; p.n_src = n_src; p.heads = heads; p.D = D; p.slope = slope;
     p.sign = mode == DGLLB_GAT_SOFTMAX ? 1.f : -1.f;
+    p.drop_thresh = drop_p > 0.f ? static_cast<unsigned>(static_cast<double>(drop_p) * 4294967296.0) : 0u;
+    if (drop_p > 0.f && p.drop_thresh == 0u) p.drop_thresh = 1u;
+    p.drop_scale = 1.f / (1.f - drop_p);
+    p.seed = drop_seed;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = aligned16(Wh) && aligned16(g) && aligned16(d_Wh) && ldw % 4 == 0 && ldg % 4 == 0 &&
                      ldd % 4 == 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(edge_ws) & 7) == 0;

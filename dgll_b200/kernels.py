@@ -278,7 +278,7 @@ def gemm(a, b, bias=None, relu=False, elu=False, trans_a=False, trans_b=False, o
 
 
 def gat_forward(row_ptr, col_idx, wh, el, er, heads, slope, mode="softmax", elu=False, save_stats=False,
-                n_dst=None, out=None, plan=None):
+                n_dst=None, out=None, plan=None, dropout=0.0, seed=0):
     """Fused multi-head GAT aggregation; ``wh`` is [n_src, heads*D], ``el``/``er`` are [n, heads]."""
     _need_cuda(row_ptr, col_idx, wh, el, er, out)
     rp, is64 = _rowptr(row_ptr)
@@ -303,13 +303,14 @@ def gat_forward(row_ptr, col_idx, wh, el, er, heads, slope, mode="softmax", elu=
     md = {"softmax": GAT_SOFTMAX, "exp_neg": GAT_EXP_NEG}[mode]
     check(lib().dgllb_gat_forward(_p(rp), is64, _p(col), _p(wh), ldw, _p(el), _p(er), lde, _p(out), ldo,
                                   _p(rmax), _p(rsum), n_dst, wh.size(0), heads, FD // heads, float(slope), md,
-                                  EPI_ELU if elu else 0, plan._h if plan is not None else None, _stream()),
+                                  EPI_ELU if elu else 0, float(dropout), ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
+                                  plan._h if plan is not None else None, _stream()),
           "gat_forward")
     return (out, rmax, rsum) if save_stats else out
 
 
 def gat_backward(row_ptr, col_idx, t_row_ptr, t_col_idx, perm, wh, el, er, out, rmax, rsum, grad_out, heads,
-                 slope, mode="softmax", d_ext=None):
+                 slope, mode="softmax", d_ext=None, dropout=0.0, seed=0):
     """Backward of :func:`gat_forward`.  Returns (d_wh, d_el, d_er) — views into one [n, heads*D+2*heads]
     buffer (``d_ext``) when n_src == n_dst so the dense-transform backward runs as one GEMM."""
     _need_cuda(row_ptr, col_idx, t_row_ptr, t_col_idx, perm, wh, el, er, out, rmax, rsum, grad_out)
@@ -342,8 +343,16 @@ def gat_backward(row_ptr, col_idx, t_row_ptr, t_col_idx, perm, wh, el, er, out, 
     check(lib().dgllb_gat_backward(_p(rp), is64, _p(col), _p(trp), _p(tcol), _p(perm), _p(wh), ldw, _p(el), _p(er),
                                    lde, _p(out), ldo, _p(rmax), _p(rsum), _p(g), ldg, _p(d_wh), ldd, _p(d_el),
                                    _p(d_er), ldde, _p(ws), n_dst, n_src, heads, FD // heads, float(slope), md,
-                                   _stream()), "gat_backward")
+                                   float(dropout), ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _stream()), "gat_backward")
     return d_wh, d_el, d_er
+
+
+def gat_dropout_mask(seed, nnz, heads, p, device="cuda"):
+    """The [nnz, heads] multiplier (0 or 1/(1-p)) the GAT kernels apply for this seed — for tests / replay."""
+    out = torch.empty((nnz, heads), dtype=torch.float32, device=device)
+    check(lib().dgllb_gat_dropout_mask(ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), nnz, heads, float(p), _p(out),
+                                       _stream()), "gat_dropout_mask")
+    return out
 
 
 def packed_words(F):

@@ -10,7 +10,8 @@ The aggregation of every layer runs on the hand-written kernels through ``dgll_b
   GinConv                      Linear(X + A·X) with the dense batched adjacency sparsified        ginconv.py:10-30
 Differences from the reference, all documented in SURVEY.md §8: ``NeighborAggregator`` really reduces over K (the
 reference discards the reduction, sageconv.py:33-38) and ``sageConv.weight`` is initialised (never is upstream);
-attention dropout (> 0 in training mode) is not implemented in the fused kernel and raises.
+attention dropout runs INSIDE the fused kernel with a counter-based mask (same distribution as ``F.dropout`` on the
+attention coefficients, not the same draws).
 """
 import math
 
@@ -161,11 +162,9 @@ class GraphSage(F.nn.Module):
 
 
 # ------------------------------------------------------------------- GAT ---
-def _check_attention_dropout(p, training):
-    if training and p > 0:
-        raise NotImplementedError(
-            "dgll_b200: attention dropout (p=%g) in training mode is not implemented in the fused GAT kernel; "
-            "use dropout=0 or eval()" % p)
+def _attn_dropout(p, training):
+    """Attention dropout probability for this call (gatconv.py:37 ``F.dropout(attention, p, training=)``, :132)."""
+    return float(p) if (training and p > 0) else 0.0
 
 
 class gatConv(F.nn.Module):
@@ -189,10 +188,10 @@ class gatConv(F.nn.Module):
         return e[:, 0:1].contiguous(), e[:, 1:2].contiguous()
 
     def forward(self, h, adj):
-        _check_attention_dropout(self.dropout, self.training)
         Wh = ops.linear(h, self.W)
         el, er = self._scores(Wh)
-        return ops.gat_aggregate(adj, Wh, el, er, heads=1, slope=self.alpha, mode="softmax", elu=self.concat)
+        return ops.gat_aggregate(adj, Wh, el, er, heads=1, slope=self.alpha, mode="softmax", elu=self.concat,
+                                 dropout=_attn_dropout(self.dropout, self.training))
 
     def __repr__(self):
         return "%s (%d -> %d)" % (self.__class__.__name__, self.in_features, self.out_features)
@@ -255,13 +254,13 @@ class sparseGatConv(F.nn.Module):
         self.special_spmm = SpecialSpmm()
 
     def forward(self, input, adj):
-        _check_attention_dropout(self.dropout.p, self.training)
         D = self.out_features
         h = ops.linear(input, self.W)
         a2 = self.a.reshape(2, D).t()                               # [D, 2]: columns a[:D], a[D:]
         e = ops.linear(h, a2)
         el, er = e[:, 0:1].contiguous(), e[:, 1:2].contiguous()
-        return ops.gat_aggregate(adj, h, el, er, heads=1, slope=self.alpha, mode="exp_neg", elu=self.concat)
+        return ops.gat_aggregate(adj, h, el, er, heads=1, slope=self.alpha, mode="exp_neg", elu=self.concat,
+                                 dropout=_attn_dropout(self.dropout.p, self.training))
 
     def __repr__(self):
         return "%s (%d -> %d)" % (self.__class__.__name__, self.in_features, self.out_features)
@@ -286,8 +285,9 @@ class _MultiHeadMixin:
         Whv = Wh.view(-1, H, D)
         el = (Whv * a_l).sum(-1)
         er = (Whv * a_r).sum(-1)
+        pdrop = atts[0].dropout.p if isinstance(atts[0].dropout, torch.nn.Dropout) else atts[0].dropout
         return ops.gat_aggregate(adj, Wh, el.contiguous(), er.contiguous(), heads=H, slope=atts[0].alpha, mode=mode,
-                                 elu=True)
+                                 elu=True, dropout=_attn_dropout(pdrop, self.training))
 
 
 class GAT(F.nn.Module, _MultiHeadMixin):
@@ -302,7 +302,6 @@ class GAT(F.nn.Module, _MultiHeadMixin):
         self.out_att = gatConv(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)
 
     def forward(self, x, adj):
-        _check_attention_dropout(self.dropout, self.training)
         x = Fn.dropout(x, self.dropout, training=self.training)
         x = self._heads_forward(x, adj, "softmax")
         x = Fn.dropout(x, self.dropout, training=self.training)
@@ -323,7 +322,6 @@ class SpGAT(F.nn.Module, _MultiHeadMixin):
         self.out_att = sparseGatConv(nhid * nheads, nclass, dropout=dropout, alpha=alpha, concat=False)
 
     def forward(self, x, adj):
-        _check_attention_dropout(self.dropout, self.training)
         x = Fn.dropout(x, self.dropout, training=self.training)
         x = self._heads_forward(x, adj, "exp_neg")
         x = Fn.dropout(x, self.dropout, training=self.training)

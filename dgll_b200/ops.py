@@ -286,10 +286,12 @@ def mm(a, b):
 # -------------------------------------------------------------------- GAT ---
 class _GatFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, wh, el, er, graph, heads, slope, mode):
+    def forward(ctx, wh, el, er, graph, heads, slope, mode, dropout, seed):
         out, rmax, rsum = K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode,
-                                        save_stats=True, n_dst=graph.n_dst, plan=graph.bin_plan())
+                                        save_stats=True, n_dst=graph.n_dst, plan=graph.bin_plan(), dropout=dropout,
+                                        seed=seed)
         ctx.graph, ctx.heads, ctx.slope, ctx.mode = graph, heads, slope, mode
+        ctx.dropout, ctx.seed = dropout, seed
         ctx.save_for_backward(wh, el, er, out, rmax, rsum)
         return out
 
@@ -299,18 +301,29 @@ class _GatFn(torch.autograd.Function):
         graph = ctx.graph
         gt = graph.transpose()
         d_wh, d_el, d_er = K.gat_backward(graph.row_ptr, graph.col, gt.row_ptr, gt.col, graph._perm, wh, el, er, out,
-                                          rmax, rsum, grad.contiguous(), ctx.heads, ctx.slope, mode=ctx.mode)
-        return d_wh, d_el, d_er, None, None, None, None
+                                          rmax, rsum, grad.contiguous(), ctx.heads, ctx.slope, mode=ctx.mode,
+                                          dropout=ctx.dropout, seed=ctx.seed)
+        return d_wh, d_el, d_er, None, None, None, None, None, None
 
 
-def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False):
-    """Fused SDDMM + edge-softmax + aggregation.  ``wh`` [n_src, heads*D]; ``el`` [n_dst, heads]; ``er`` [n_src, heads]."""
+def _fresh_seed():
+    """64-bit seed from torch's CPU generator (follows torch.manual_seed; no device synchronisation)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False, dropout=0.0, seed=None):
+    """Fused SDDMM + edge-softmax + aggregation.  ``wh`` [n_src, heads*D]; ``el`` [n_dst, heads]; ``er`` [n_src, heads].
+    ``dropout`` > 0 drops attention coefficients inside the kernel (mask = f(seed, edge, head), replayed by the
+    backward) exactly where the reference applies ``F.dropout`` to them (gatconv.py:37, :132)."""
     graph = as_csr(adj, binary=True)
+    if dropout and seed is None:
+        seed = _fresh_seed()
+    seed = seed or 0
     if torch.is_grad_enabled() and (wh.requires_grad or el.requires_grad or er.requires_grad):
-        out = _GatFn.apply(wh, el, er, graph, heads, slope, mode)
+        out = _GatFn.apply(wh, el, er, graph, heads, slope, mode, float(dropout), seed)
         return torch.nn.functional.elu(out) if elu else out
     return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst,
-                         plan=graph.bin_plan())
+                         plan=graph.bin_plan(), dropout=float(dropout), seed=seed)
 
 
 # -------------------------------------------------------------- binarized ---

@@ -244,6 +244,9 @@ int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const int32_t* col_
                       int64_t ld_e, float* out, int64_t ldo, float* row_max, float* row_sum,
                       int64_t n_dst, int64_t n_src, int heads, int D, float slope,
                       int mode, int epilogue,
+                      float drop_p /* attention dropout (gatconv.py:37, :132): applied to the normalised attention, the
+                                      row sum keeps every edge; 0 = off */,
+                      uint64_t drop_seed /* mask = f(seed, edge position in the CSR, head): reproducible in the backward */,
                       const dgllb_csr_plan* plan /* optional: long rows are split into chunks whose partial softmax
                                                     states are merged exactly (no atomics) */,
                       void* stream);
@@ -267,7 +270,11 @@ int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const int32_t* col
                        const float* row_sum, const float* g, int64_t ldg, float* d_Wh,
                        int64_t ldd, float* d_el, float* d_er, int64_t ld_de, float* edge_ws,
                        int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                       int mode, void* stream);
+                       int mode, float drop_p, uint64_t drop_seed /* the forward's values */, void* stream);
+
+/* mask_out[e*heads + h] = 0 (dropped) or 1/(1-drop_p) (kept): the multiplier the GAT kernels apply to edge e, head h
+ * for this seed.  Test / debugging aid: lets a host restatement replay the exact mask. */
+int dgllb_gat_dropout_mask(uint64_t drop_seed, int64_t nnz, int heads, float drop_p, float* mask_out, void* stream);
 
 /* ------------------------------------------------- binarized aggregation -- */
 

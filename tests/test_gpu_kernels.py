@@ -716,3 +716,52 @@ def test_device_block_builder_matches_sort_based_compaction(K, fanouts):
     rp0 = torch.zeros(4, dtype=torch.int32, device="cuda")
     s, c, cnt = K.build_block(torch.tensor([7, 3, 9], device="cuda"), rp0, torch.zeros(0, dtype=torch.int32, device="cuda"))
     assert cnt.tolist() == [3, 0] and s[:3].tolist() == [7, 3, 9]
+
+
+# ------------------------------------------------------ attention dropout --
+@pytest.mark.parametrize("kernel", ["group", "row"])
+@pytest.mark.parametrize("mode", ["softmax", "exp_neg"])
+def test_gat_attention_dropout_forward_backward_with_replayed_mask(K, kernel, mode, monkeypatch):
+    """The kernels' dropout mask is exported (dgllb_gat_dropout_mask) and replayed in an fp64 autograd restatement of
+    gatconv.py:30-54 / :111-148 WITH dropout on the attention coefficients: outputs and all three gradients match."""
+    monkeypatch.setenv("DGLLB_GAT_KERNEL", kernel)
+    rng = np.random.default_rng(3)
+    n, heads, D, pdrop, seed = 300, 4, 32, 0.4, 123456789
+    rp, col = rand_csr(rng, n, n, 25, heavy=[(9, 400)])
+    wh = rng.standard_normal((n, heads * D)).astype(np.float32)
+    el = rng.standard_normal((n, heads)).astype(np.float32)
+    er = rng.standard_normal((n, heads)).astype(np.float32)
+    g = rng.standard_normal((n, heads * D)).astype(np.float32)
+    mask = K.gat_dropout_mask(seed, col.size, heads, pdrop)
+    kept = (mask > 0).float().mean().item()
+    assert abs(kept - (1 - pdrop)) < 0.02 and torch.all((mask == 0) | ((mask - 1 / (1 - pdrop)).abs() < 1e-6))
+    rows = torch.from_numpy(np.repeat(np.arange(n), rp[1:] - rp[:-1])).long()
+    cols = torch.from_numpy(col).long()
+    twh = torch.from_numpy(wh).double().requires_grad_(True)
+    tel = torch.from_numpy(el).double().requires_grad_(True)
+    ter = torch.from_numpy(er).double().requires_grad_(True)
+    z = torch.nn.functional.leaky_relu(tel[rows] + ter[cols], 0.2)
+    sgn = z if mode == "softmax" else -z
+    smax = torch.full((n, heads), -float("inf"), dtype=torch.float64).scatter_reduce(
+        0, rows[:, None].expand(-1, heads), sgn.detach(), reduce="amax")
+    ex = torch.exp(sgn - smax[rows])
+    den = torch.zeros(n, heads, dtype=torch.float64).index_add_(0, rows, ex)
+    alpha = ex / den[rows] * mask.double().cpu()                 # dropout AFTER normalisation, as the reference
+    msg = alpha[:, :, None] * twh[cols].view(-1, heads, D)
+    ref = torch.zeros(n, heads, D, dtype=torch.float64).index_add_(0, rows, msg).view(n, heads * D)
+    ref.backward(torch.from_numpy(g).double())
+    drp, dcol = dev(rp), dev(col)
+    plan = K.CsrPlan(drp, chunk_edges=128) if kernel == "row" else None
+    out, rmax, rsum = K.gat_forward(drp, dcol, dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, save_stats=True,
+                                    dropout=pdrop, seed=seed, plan=plan)
+    assert rel_err(out.cpu().numpy(), ref.detach().numpy()) <= FP32_TOL
+    trp, tcol, _, perm = K.csr_transpose(drp, dcol, n, want_perm=True)
+    d_wh, d_el, d_er = K.gat_backward(drp, dcol, trp, tcol, perm, dev(wh), dev(el), dev(er), out, rmax, rsum, dev(g),
+                                      heads, 0.2, mode=mode, dropout=pdrop, seed=seed)
+    assert rel_err(d_wh.cpu().numpy(), twh.grad.numpy()) <= 2e-5
+    assert rel_err(d_el.cpu().numpy(), tel.grad.numpy()) <= 2e-5
+    assert rel_err(d_er.cpu().numpy(), ter.grad.numpy()) <= 2e-5
+    # p = 0 is bit-identical to the call without dropout arguments
+    a = K.gat_forward(drp, dcol, dev(wh), dev(el), dev(er), heads, 0.2, mode=mode)
+    b = K.gat_forward(drp, dcol, dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, dropout=0.0, seed=99)
+    assert torch.equal(a, b)

@@ -157,10 +157,33 @@ def test_gat_models_match_reference_golden(nn, tag, cls):
     assert rel_err(first.cpu(), g["first_layer"]) <= OUT_TOL
 
 
-def test_attention_dropout_in_training_raises(nn):
-    m = nn.gatConv(8, 4, dropout=0.6, alpha=0.2).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(5, 8, device="cuda"), torch.eye(5, device="cuda"))
+def test_attention_dropout_in_training_mode(nn):
+    """gatconv.py:37 / :132: dropout on the attention coefficients in training mode.  The fused kernel draws its own
+    counter-based mask: eval mode is deterministic and equals p=0; training mode differs call to call, follows
+    torch.manual_seed, keeps the expectation, and backpropagates."""
+    torch.manual_seed(0)
+    n = 400
+    adj = (torch.rand(n, n, device="cuda") < 0.05).float()
+    adj.fill_diagonal_(1.0)
+    x = torch.randn(n, 16, device="cuda")
+    for cls in (nn.gatConv, nn.sparseGatConv):
+        m = cls(16, 8, dropout=0.6, alpha=0.2).cuda()
+        m.eval()
+        e1, e2 = m(x, adj), m(x, adj)
+        assert torch.equal(e1, e2)
+        m.train()
+        torch.manual_seed(1)
+        t1 = m(x, adj)
+        t2 = m(x, adj)
+        torch.manual_seed(1)
+        t3 = m(x, adj)
+        assert not torch.equal(t1, t2) and torch.equal(t1, t3) and not torch.equal(t1, e1)
+        t1.sum().backward()
+        assert torch.isfinite(m.W.grad).all() and torch.isfinite(m.a.grad).all()
+    model = nn.SpGAT(16, 8, 5, dropout=0.6, alpha=0.2, nheads=4).cuda().train()
+    out = model(x, adj)
+    torch.nn.functional.nll_loss(out, torch.randint(0, 5, (n,), device="cuda")).backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())
 
 
 def test_special_spmm_matches_reference_golden(nn):
