@@ -464,6 +464,7 @@ def main():
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res[prec] = {"epoch_s_sampler_in_loop": round(t[0].item(), 4), "epoch_s_presampled": round(t[1].item(), 4),
+
                          "batches_per_gpu": r_e2e["n_batches"], "loss": round(r_e2e["loss"], 4)}
         epoch = {"model": "GraphSAGE-mean 2-layer 602-256-41, fanout 25/10, batch 1024/GPU, Adam, fwd+bwd+step",
                  "train_seeds": int(perm.numel()), "gemm": res}

@@ -57,3 +57,26 @@ def sage_epoch(model, opt, table, labels, n_feat, row_ptr=None, col_idx=None, se
         ops.set_gemm_precision(prev)
     return {"time_s": e0.elapsed_time(e1) * 1e-3, "wall_s": time.perf_counter() - t_wall, "n_batches": n,
             "loss": float(loss_sum.item()) / max(n, 1)}
+
+
+def sage_epoch_pipelined(model, opt, table, labels, row_ptr, col_idx, seeds, fanouts=(25, 10), batch_size=1024,
+                         rng_seed=0, group=None, precision=None, buffer_size=4):
+    """The same epoch as ``sage_epoch`` (sampler in the loop) run through the MQ-GNN style producer/consumer pipeline
+    (``dgll_b200.pipeline``): sampling + block construction on a producer thread / stream, training on the consumer."""
+    from . import pipeline
+
+    if precision is not None:
+        prev = ops.get_gemm_precision()
+        ops.set_gemm_precision(precision)
+
+    def batches():
+        for b, i in enumerate(range(0, seeds.numel(), batch_size)):
+            s = seeds[i:i + batch_size]
+            blocks = G.sample_blocks(row_ptr, col_idx, s, fanouts, rng_seed=rng_seed * 7919 + b)
+            yield blocks[0].src_ids, s, blocks
+
+    res = pipeline.run_epoch(batches(), model, opt, fetch=None, labels=labels, group=group, BUFFER_SIZE=buffer_size,
+                             forward=lambda m, mfgs, feat: m(mfgs, None, feat_table=table))
+    if precision is not None:
+        ops.set_gemm_precision(prev)
+    return res

@@ -510,3 +510,28 @@ def test_normalisation_helpers_match_reference():
     dense[rows, sv.col.long()] = sv.values
     assert rel_err(dense.cpu().numpy(), ref) <= 1e-6
     assert rel_err(np.asarray(U.normalize_lap(sp.csr_matrix(a)).todense()), ref) <= 1e-6
+
+
+# ------------------------------------------------------------ pipeline -----
+def test_pipelined_epoch_equals_sequential_epoch(nn):
+    """MQ-GNN style producer/consumer epoch (dgll_b200.pipeline) == the sequential loop on the same seeds: every kernel
+    on the path is deterministic, so the losses and the final weights agree bit for bit."""
+    import copy
+    from dgll_b200 import graphs as G, train as T
+    N, F = 20000, 100
+    rp, col = G.rmat_csr(N, N * 20, seed=1, device="cuda")
+    table = G.feature_table(N, F, seed=2)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    labels = torch.randint(0, 7, (N,), device="cuda", generator=gen)
+    seeds = torch.randperm(N, device="cuda", generator=gen)[:1024 * 6]
+    torch.manual_seed(0)
+    m1 = nn.GraphSAGE(F, 64, 7, 2, torch.relu, 0.0).cuda()
+    m2 = copy.deepcopy(m1)
+    o1 = torch.optim.SGD(m1.parameters(), lr=0.05)
+    o2 = torch.optim.SGD(m2.parameters(), lr=0.05)
+    a = T.sage_epoch(m1, o1, table, labels, F, rp, col, seeds, (10, 5), 1024, rng_seed=4)
+    b = T.sage_epoch_pipelined(m2, o2, table, labels, rp, col, seeds, (10, 5), 1024, rng_seed=4)
+    assert a["n_batches"] == b["n_batches"] == 6
+    assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"])
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        assert torch.equal(p, q)
