@@ -45,7 +45,7 @@ SIGNATURES = {
                                c_uint64, _P, _P]),
     "dgllb_gat_dropout_mask": (_I, [c_uint64, _L, _I, c_float, _P, _P]),
     "dgllb_gat_backward": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _P, _L, _P, _P, _P, _L, _P, _L,
-                                _P, _P, _L, _P, _L, _L, _I, _I, c_float, _I, c_float, c_uint64, _P]),
+                                _P, _P, _L, _P, _L, _L, _I, _I, c_float, _I, c_float, c_uint64, _P, _P, _P]),
     "dgllb_binarize_pack": (_I, [_P, _L, _P, _L, _L, _I, _P]),
     "dgllb_bin_spmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
     "dgllb_sample_neighbors": (_I, [_P, _I, _P, _P, _I, _L, _I, c_uint64, _P, _P, _P]),

@@ -466,20 +466,43 @@ struct GatBwdParams {
     unsigned drop_thresh;  // same mask as the forward (seed, edge position, head)
     float drop_scale;
     unsigned long long seed;
+    // nnz-split of long rows: pass 1 over the forward CSR (e_*), pass 2 over the transposed CSR (t_*).
+    // Partial results go to workspaces and are merged by gat_bwd_combine_* (deterministic, no atomics).
+    int e_chunk;
+    const int2* e_items;
+    long long e_n_items;
+    float* e_ws;          // [e_n_items, heads]        partial d_el
+    int t_chunk;
+    const int2* t_items;
+    long long t_n_items;
+    float* t_ws;          // [t_n_items, heads*D + heads]  partial d_Wh rows, then partial d_er
 };
 
 // Pass 1: group = (dst row i, head).  Lane columns: chunk k covers (k*LANES + lig)*VE.
-template <int VE, int LANES, int NCH>
+template <int VE, int LANES, int NCH, bool HEAVY>
 __global__ void __launch_bounds__(kGatThreads)
 gat_backward_edge_kernel(const GatBwdParams p) {
     const int lig = threadIdx.x & (LANES - 1);
     const long long group = (static_cast<long long>(blockIdx.x) * kGatThreads + threadIdx.x) / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                          : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
-    const long long row = group / p.heads;
-    if (row >= p.n_dst) return;
-    const int head = static_cast<int>(group - row * p.heads);
-    const long long beg = gat_rp(p.row_ptr, p.rp64, row), end = gat_rp(p.row_ptr, p.rp64, row + 1);
+    const long long unit = group / p.heads;       // dst row, or plan item (row, chunk) when HEAVY
+    const int head = static_cast<int>(group - unit * p.heads);
+    long long row, beg, end;
+    if (HEAVY) {
+        if (unit >= p.e_n_items) return;
+        const int2 it = p.e_items[unit];
+        row = it.x;
+        const long long rb = gat_rp(p.row_ptr, p.rp64, row), re = gat_rp(p.row_ptr, p.rp64, row + 1);
+        beg = rb + static_cast<long long>(it.y) * p.e_chunk;
+        end = min(re, beg + p.e_chunk);
+    } else {
+        row = unit;
+        if (row >= p.n_dst) return;
+        beg = gat_rp(p.row_ptr, p.rp64, row);
+        end = gat_rp(p.row_ptr, p.rp64, row + 1);
+        if (p.e_chunk > 0 && end - beg > p.e_chunk) return;  // done by the heavy items
+    }
 
     float gi[NCH][VE];
     float c_part = 0.f;
@@ -561,11 +584,14 @@ gat_backward_edge_kernel(const GatBwdParams p) {
         }
     }
     const float del = group_sum<LANES>(del_acc, gmask);
-    if (lig == 0) p.d_el[row * p.ld_de + head] = del;
+    if (lig == 0) {
+        if (HEAVY) p.e_ws[unit * p.heads + head] = del;
+        else p.d_el[row * p.ld_de + head] = del;
+    }
 }
 
 // Pass 2: group = (src row j, head, slab) over the transposed CSR.
-template <int VE, int LANES>
+template <int VE, int LANES, bool HEAVY>
 __global__ void __launch_bounds__(kGatThreads)
 gat_backward_node_kernel(const GatBwdParams p, int n_slabs) {
     const int lig = threadIdx.x & (LANES - 1);
@@ -573,12 +599,25 @@ gat_backward_node_kernel(const GatBwdParams p, int n_slabs) {
     const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                          : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
     const int per_row = p.heads * n_slabs;
-    const long long row = group / per_row;
-    if (row >= p.n_src) return;
-    const int rem = static_cast<int>(group - row * per_row);
+    const long long unit = group / per_row;       // src row of the transposed CSR, or plan item when HEAVY
+    const int rem = static_cast<int>(group - unit * per_row);
     const int head = rem / n_slabs;
     const int slab = rem - head * n_slabs;
-    const long long beg = gat_rp(p.t_row_ptr, p.rp64, row), end = gat_rp(p.t_row_ptr, p.rp64, row + 1);
+    long long row, beg, end;
+    if (HEAVY) {
+        if (unit >= p.t_n_items) return;
+        const int2 it = p.t_items[unit];
+        row = it.x;
+        const long long rb = gat_rp(p.t_row_ptr, p.rp64, row), re = gat_rp(p.t_row_ptr, p.rp64, row + 1);
+        beg = rb + static_cast<long long>(it.y) * p.t_chunk;
+        end = min(re, beg + p.t_chunk);
+    } else {
+        row = unit;
+        if (row >= p.n_src) return;
+        beg = gat_rp(p.t_row_ptr, p.rp64, row);
+        end = gat_rp(p.t_row_ptr, p.rp64, row + 1);
+        if (p.t_chunk > 0 && end - beg > p.t_chunk) return;  // done by the heavy items
+    }
     const int dcol = (slab * LANES + lig) * VE;
     const bool lane_on = dcol < p.D;
     const float* __restrict__ gb = p.g + head * p.D + dcol;
@@ -626,14 +665,19 @@ gat_backward_node_kernel(const GatBwdParams p, int n_slabs) {
             }
         }
     }
+    const long long FDh = static_cast<long long>(p.heads) * p.D;
     if (slab == 0) {
         const float der = group_sum<LANES>(der_acc, gmask);
-        if (lig == 0) p.d_er[row * p.ld_de + head] = der;
+        if (lig == 0) {
+            if (HEAVY) p.t_ws[unit * (FDh + p.heads) + FDh + head] = der;
+            else p.d_er[row * p.ld_de + head] = der;
+        }
     }
     if (!lane_on) return;
-    float* __restrict__ o = p.d_Wh + row * p.ldd + head * p.D + dcol;
+    float* __restrict__ o = HEAVY ? p.t_ws + unit * (FDh + p.heads) + head * p.D + dcol
+                                  : p.d_Wh + row * p.ldd + head * p.D + dcol;
     const int valid = min(VE, p.D - dcol);
-    if (VE == 4 && valid == 4) {
+    if (VE == 4 && valid == 4 && !HEAVY) {
         stg_cs_f4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
     } else {
 #pragma unroll
@@ -642,16 +686,49 @@ gat_backward_node_kernel(const GatBwdParams p, int n_slabs) {
     }
 }
 
-template <int VE, int LANES>
+// merge the partials of the long rows: one thread block per k == 0 item (its chunks are items [w, w + nc))
+__global__ void gat_bwd_combine_edge_kernel(const GatBwdParams p) {
+    const long long w = blockIdx.x;
+    if (w >= p.e_n_items) return;
+    const int2 it = p.e_items[w];
+    if (it.y != 0) return;
+    const long long row = it.x;
+    const long long deg = gat_rp(p.row_ptr, p.rp64, row + 1) - gat_rp(p.row_ptr, p.rp64, row);
+    const int nc = static_cast<int>((deg + p.e_chunk - 1) / p.e_chunk);
+    for (int h = threadIdx.x; h < p.heads; h += blockDim.x) {
+        float sacc = 0.f;
+        for (int c = 0; c < nc; ++c) sacc += p.e_ws[(w + c) * p.heads + h];
+        p.d_el[row * p.ld_de + h] = sacc;
+    }
+}
+__global__ void gat_bwd_combine_node_kernel(const GatBwdParams p) {
+    const long long w = blockIdx.x;
+    if (w >= p.t_n_items) return;
+    const int2 it = p.t_items[w];
+    if (it.y != 0) return;
+    const long long row = it.x;
+    const long long deg = gat_rp(p.t_row_ptr, p.rp64, row + 1) - gat_rp(p.t_row_ptr, p.rp64, row);
+    const int nc = static_cast<int>((deg + p.t_chunk - 1) / p.t_chunk);
+    const long long FDh = static_cast<long long>(p.heads) * p.D, W = FDh + p.heads;
+    for (long long f = threadIdx.x; f < W; f += blockDim.x) {
+        float sacc = 0.f;
+        for (int c = 0; c < nc; ++c) sacc += p.t_ws[(w + c) * W + f];
+        if (f < FDh) p.d_Wh[row * p.ldd + f] = sacc;
+        else p.d_er[row * p.ld_de + (f - FDh)] = sacc;
+    }
+}
+
+template <int VE, int LANES, bool HEAVY>
 static int launch_gat_bwd_edge(const GatBwdParams& p, int nch, cudaStream_t st) {
-    const long long groups = p.n_dst * p.heads;
+    const long long groups = (HEAVY ? p.e_n_items : p.n_dst) * p.heads;
+    if (groups == 0) return DGLLB_OK;
     const int gpb = kGatThreads / LANES;
     const long long blocks = (groups + gpb - 1) / gpb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
     const unsigned g = static_cast<unsigned>(blocks);
-    if (nch <= 1) gat_backward_edge_kernel<VE, LANES, 1><<<g, kGatThreads, 0, st>>>(p);
-    else if (nch <= 2) gat_backward_edge_kernel<VE, LANES, 2><<<g, kGatThreads, 0, st>>>(p);
-    else if (nch <= 4) gat_backward_edge_kernel<VE, LANES, 4><<<g, kGatThreads, 0, st>>>(p);
+    if (nch <= 1) gat_backward_edge_kernel<VE, LANES, 1, HEAVY><<<g, kGatThreads, 0, st>>>(p);
+    else if (nch <= 2) gat_backward_edge_kernel<VE, LANES, 2, HEAVY><<<g, kGatThreads, 0, st>>>(p);
+    else if (nch <= 4) gat_backward_edge_kernel<VE, LANES, 4, HEAVY><<<g, kGatThreads, 0, st>>>(p);
     else {
         set_error("gat_backward: head width D=%d too large for this build", p.D);
         return DGLLB_ERR_UNSUPPORTED;
@@ -660,31 +737,72 @@ static int launch_gat_bwd_edge(const GatBwdParams& p, int nch, cudaStream_t st) 
     return DGLLB_OK;
 }
 
+template <int VE, int LANES, bool HEAVY>
+static int launch_gat_bwd_node(const GatBwdParams& p, int nch, cudaStream_t st) {
+    const long long groups = (HEAVY ? p.t_n_items : p.n_src) * p.heads * nch;
+    if (groups == 0) return DGLLB_OK;
+    const int gpb = kGatThreads / LANES;
+    const long long blocks = (groups + gpb - 1) / gpb;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
+    gat_backward_node_kernel<VE, LANES, HEAVY><<<static_cast<unsigned>(blocks), kGatThreads, 0, st>>>(p, nch);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+template <int VE, int LANES>
+static int launch_gat_bwd_lanes(const GatBwdParams& p, int nch, cudaStream_t st) {
+    int rc;
+    if (p.e_n_items > 0) {
+        if ((rc = launch_gat_bwd_edge<VE, LANES, true>(p, nch, st)) != DGLLB_OK) return rc;
+    }
+    if ((rc = launch_gat_bwd_edge<VE, LANES, false>(p, nch, st)) != DGLLB_OK) return rc;
+    if (p.e_n_items > 0) {
+        gat_bwd_combine_edge_kernel<<<static_cast<unsigned>(p.e_n_items), 32, 0, st>>>(p);
+        DGLLB_LAUNCH_CHECK();
+    }
+    if (p.t_n_items > 0) {
+        if ((rc = launch_gat_bwd_node<VE, LANES, true>(p, nch, st)) != DGLLB_OK) return rc;
+    }
+    if ((rc = launch_gat_bwd_node<VE, LANES, false>(p, nch, st)) != DGLLB_OK) return rc;
+    if (p.t_n_items > 0) {
+        gat_bwd_combine_node_kernel<<<static_cast<unsigned>(p.t_n_items), 256, 0, st>>>(p);
+        DGLLB_LAUNCH_CHECK();
+    }
+    return DGLLB_OK;
+}
+
 template <int VE>
-static int launch_gat_bwd(const GatBwdParams& p, cudaStream_t st) {
+static int launch_gat_bwd(GatBwdParams& p, const dgllb_csr_plan* plan, const dgllb_csr_plan* t_plan, cudaStream_t st) {
     int lanes = 32;
     if (VE > 1 && p.D <= 8 * VE) lanes = 8;
     else if (VE > 1 && p.D <= 16 * VE) lanes = 16;
     const int nch = (p.D + lanes * VE - 1) / (lanes * VE);
+    const bool eh = plan && plan->n_heavy_rows > 0, th = t_plan && t_plan->n_heavy_rows > 0;
+    p.e_chunk = eh ? plan->chunk_edges : 0;
+    p.e_items = eh ? plan->items : nullptr;
+    p.e_n_items = eh ? plan->n_items : 0;
+    p.t_chunk = th ? t_plan->chunk_edges : 0;
+    p.t_items = th ? t_plan->items : nullptr;
+    p.t_n_items = th ? t_plan->n_items : 0;
+    p.e_ws = p.t_ws = nullptr;
+    char* ws = nullptr;
+    const size_t FDh = static_cast<size_t>(p.heads) * p.D;
+    const size_t b_e = (sizeof(float) * static_cast<size_t>(p.e_n_items) * p.heads + 255) & ~static_cast<size_t>(255);
+    const size_t b_t = sizeof(float) * static_cast<size_t>(p.t_n_items) * (FDh + p.heads);
+    if (eh || th) {
+        DevInfo di_;
+        int rc_ = get_devinfo(&di_);
+        if (rc_ != DGLLB_OK) return rc_;
+        DGLLB_CUDA_TRY(cudaMallocAsync(&ws, b_e + b_t + 256, st));
+        p.e_ws = reinterpret_cast<float*>(ws);
+        p.t_ws = reinterpret_cast<float*>(ws + b_e);
+    }
     int rc;
-    if (p.n_dst > 0) {
-        if (lanes == 8) rc = launch_gat_bwd_edge<VE, 8>(p, nch, st);
-        else if (lanes == 16) rc = launch_gat_bwd_edge<VE, 16>(p, nch, st);
-        else rc = launch_gat_bwd_edge<VE, 32>(p, nch, st);
-        if (rc != DGLLB_OK) return rc;
-    }
-    if (p.n_src > 0) {
-        const long long groups = p.n_src * p.heads * nch;
-        const int gpb = kGatThreads / lanes;
-        const long long blocks = (groups + gpb - 1) / gpb;
-        DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
-        const unsigned g = static_cast<unsigned>(blocks);
-        if (lanes == 8) gat_backward_node_kernel<VE, 8><<<g, kGatThreads, 0, st>>>(p, nch);
-        else if (lanes == 16) gat_backward_node_kernel<VE, 16><<<g, kGatThreads, 0, st>>>(p, nch);
-        else gat_backward_node_kernel<VE, 32><<<g, kGatThreads, 0, st>>>(p, nch);
-        DGLLB_LAUNCH_CHECK();
-    }
-    return DGLLB_OK;
+    if (lanes == 8) rc = launch_gat_bwd_lanes<VE, 8>(p, nch, st);
+    else if (lanes == 16) rc = launch_gat_bwd_lanes<VE, 16>(p, nch, st);
+    else rc = launch_gat_bwd_lanes<VE, 32>(p, nch, st);
+    if (ws) cudaFreeAsync(ws, st);
+    return rc;
 }
 
 template <int VE>
@@ -811,8 +929,11 @@ extern "C" int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const i
                                   const float* row_sum, const float* g, int64_t ldg, float* d_Wh,
                                   int64_t ldd, float* d_el, float* d_er, int64_t ld_de, float* edge_ws,
                                   int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                                  int mode, float drop_p, uint64_t drop_seed, void* stream) {
+                                  int mode, float drop_p, uint64_t drop_seed, const dgllb_csr_plan* plan,
+                                  const dgllb_csr_plan* t_plan, void* stream) {
     DGLLB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "gat_backward: dropout probability must be in [0, 1)");
+    DGLLB_REQUIRE((!plan || plan->n_rows == n_dst) && (!t_plan || t_plan->n_rows == n_src),
+                  "gat_backward: plan built for another row count");
     DGLLB_REQUIRE(n_dst >= 0 && n_src >= 0 && heads >= 1 && D >= 1, "gat_backward: bad sizes");
     if (n_dst == 0 && n_src == 0) return DGLLB_OK;
     DGLLB_REQUIRE(row_ptr && t_row_ptr && Wh && el && er && out && row_max && row_sum && g && d_Wh && d_el &&
@@ -836,5 +957,5 @@ extern "C" int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = aligned16(Wh) && aligned16(g) && aligned16(d_Wh) && ldw % 4 == 0 && ldg % 4 == 0 &&
                      ldd % 4 == 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(edge_ws) & 7) == 0;
-    return vec ? launch_gat_bwd<4>(p, st) : launch_gat_bwd<1>(p, st);
+    return vec ? launch_gat_bwd<4>(p, plan, t_plan, st) : launch_gat_bwd<1>(p, plan, t_plan, st);
 }

@@ -310,7 +310,7 @@ def gat_forward(row_ptr, col_idx, wh, el, er, heads, slope, mode="softmax", elu=
 
 
 def gat_backward(row_ptr, col_idx, t_row_ptr, t_col_idx, perm, wh, el, er, out, rmax, rsum, grad_out, heads,
-                 slope, mode="softmax", d_ext=None, dropout=0.0, seed=0):
+                 slope, mode="softmax", d_ext=None, dropout=0.0, seed=0, plan=None, t_plan=None):
     """Backward of :func:`gat_forward`.  Returns (d_wh, d_el, d_er) — views into one [n, heads*D+2*heads]
     buffer (``d_ext``) when n_src == n_dst so the dense-transform backward runs as one GEMM."""
     _need_cuda(row_ptr, col_idx, t_row_ptr, t_col_idx, perm, wh, el, er, out, rmax, rsum, grad_out)
@@ -343,7 +343,9 @@ def gat_backward(row_ptr, col_idx, t_row_ptr, t_col_idx, perm, wh, el, er, out, 
     check(lib().dgllb_gat_backward(_p(rp), is64, _p(col), _p(trp), _p(tcol), _p(perm), _p(wh), ldw, _p(el), _p(er),
                                    lde, _p(out), ldo, _p(rmax), _p(rsum), _p(g), ldg, _p(d_wh), ldd, _p(d_el),
                                    _p(d_er), ldde, _p(ws), n_dst, n_src, heads, FD // heads, float(slope), md,
-                                   float(dropout), ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _stream()), "gat_backward")
+                                   float(dropout), ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
+                                   plan._h if plan is not None else None, t_plan._h if t_plan is not None else None,
+                                   _stream()), "gat_backward")
     return d_wh, d_el, d_er
 
 

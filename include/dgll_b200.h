@@ -260,6 +260,9 @@ int dgllb_gat_forward(const void* row_ptr, int row_ptr_is64, const int32_t* col_
  * float[2*nnz*heads] (8-byte aligned); pass 2 runs over the transposed CSR
  * (t_row_ptr/t_col_idx/perm from dgllb_csr_transpose) and accumulates
  * d_Wh_j = sum_i alpha_ij g_i and d_er_j.  No atomics: deterministic.
+ * `plan` (built on row_ptr) / `t_plan` (built on t_row_ptr), both optional, split
+ * rows longer than their chunk_edges into (row, chunk) items whose partial sums
+ * go to an internal workspace and are merged in a fixed order (still no atomics).
  * `out` is the forward output BEFORE the epilogue activation.
  * Replaces SpecialSpmmFunction.backward gatconv.py:71-81 + autograd of :117-139.
  */
@@ -270,7 +273,8 @@ int dgllb_gat_backward(const void* row_ptr, int row_ptr_is64, const int32_t* col
                        const float* row_sum, const float* g, int64_t ldg, float* d_Wh,
                        int64_t ldd, float* d_el, float* d_er, int64_t ld_de, float* edge_ws,
                        int64_t n_dst, int64_t n_src, int heads, int D, float slope,
-                       int mode, float drop_p, uint64_t drop_seed /* the forward's values */, void* stream);
+                       int mode, float drop_p, uint64_t drop_seed /* the forward's values */,
+                       const dgllb_csr_plan* plan, const dgllb_csr_plan* t_plan, void* stream);
 
 /* mask_out[e*heads + h] = 0 (dropped) or 1/(1-drop_p) (kept): the multiplier the GAT kernels apply to edge e, head h
  * for this seed.  Test / debugging aid: lets a host restatement replay the exact mask. */

@@ -187,6 +187,20 @@ def main():
         # bytes: pass 1 reads Wh_j + writes 8 B/(edge, head); pass 2 reads g_i + 8 B/(edge, head) per transposed edge
         bwd_bytes = nnz * (4 + heads * D * 4 + heads * 8) * 2 + Np * (heads * D * 4) * 3
         report("gat_backward (2 passes, no atomics)", "products-shaped", ms, bwd_bytes, {"csr_transpose_ms_once": round(ms_t, 3)})
+        tplan = K.CsrPlan(trp, chunk_edges=1024)
+        for ce in (1024, 256):
+            pl, tpl = K.CsrPlan(rp, chunk_edges=ce), K.CsrPlan(trp, chunk_edges=ce)
+            ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
+                                               plan=pl, t_plan=tpl), 5)
+            report("gat_backward[plans %d]" % ce, "products-shaped", ms, bwd_bytes,
+                   {"heavy_rows": pl.n_heavy_rows, "chunks": pl.n_chunks, "t_heavy_rows": tpl.n_heavy_rows,
+                    "t_chunks": tpl.n_chunks})
+        ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
+                                           plan=gplan), 5)
+        report("gat_backward[plan pass 1 only]", "products-shaped", ms, bwd_bytes)
+        ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
+                                           t_plan=tplan), 5)
+        report("gat_backward[plan pass 2 only]", "products-shaped", ms, bwd_bytes)
 
 
 if __name__ == "__main__":
