@@ -50,6 +50,13 @@ SIGNATURES = {
     "dgllb_bin_spmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
     "dgllb_sample_neighbors": (_I, [_P, _I, _P, _P, _I, _L, _I, c_uint64, _P, _P, _P]),
     "dgllb_build_block": (_I, [_P, _L, _P, _P, _L, _P, _P, _P, _P]),
+    "dgllb_csr_slice_rows_ptr": (_I, [_P, _I, _P, _L, _P, _P]),
+    "dgllb_csr_slice_rows_fill": (_I, [_P, _I, _P, _P, _P, _L, _P, _P, _P, _P]),
+    "dgllb_col_sqsum": (_I, [_P, _P, _L, _L, _I, _P, _P, _P, _P]),
+    "dgllb_weighted_choice": (_I, [_P, _P, _L, _I, c_uint64, _P, _P, _P, _P]),
+    "dgllb_importance_scale": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
+    "dgllb_scatter_pos": (_I, [_P, _P, _P, _L, _I, _P]),
+    "dgllb_csr_select_cols": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P]),
     "launch_gcn_fused_kernel": (None, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "launch_gcn_fused_kernel_backward_optimized": (None, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "dgllb_gcn_fused_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

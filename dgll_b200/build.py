@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libdgll_b200.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 SOURCES = [
     "runtime.cu", "spmm.cu", "spmm_bulk.cu", "gather.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "gemm.cu",
-    "transpose.cu", "legacy.cu", "gat.cu", "binspmm.cu", "sampler.cu", "peer.cu", "block.cu",
+    "transpose.cu", "legacy.cu", "gat.cu", "binspmm.cu", "sampler.cu", "peer.cu", "block.cu", "layerwise.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -430,6 +430,108 @@ def build_block(dst_ids, row_ptr, nbr_global):
     return src_ids, col_local, counts
 
 
+# ------------------------------------------- layer-wise importance sampling ---
+def csr_slice_rows(row_ptr, col_idx, values, rows):
+    """Q = M[rows, :] on the device.  Returns (q_row_ptr int64[n+1], q_col int32[nnz], q_values f64[nnz] | None);
+    one read-back (nnz) to size the outputs."""
+    _need_cuda(row_ptr, col_idx, values, rows)
+    rp, is64 = _rowptr(row_ptr)
+    col = _index32(col_idx, "col_idx")
+    rows = rows.to(torch.int64).contiguous()
+    n = rows.numel()
+    dev = col.device
+    q_rp = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    check(lib().dgllb_csr_slice_rows_ptr(_p(rp), is64, _p(rows), n, _p(q_rp), _stream()), "csr_slice_rows")
+    nnz = int(q_rp[-1].item())
+    q_col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    q_val = None
+    if values is not None:
+        if values.dtype != torch.float64:
+            raise TypeError("csr_slice_rows: values must be float64 (the Laplacian's dtype)")
+        values = values.contiguous()
+        q_val = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)[:nnz]
+    check(lib().dgllb_csr_slice_rows_fill(_p(rp), is64, _p(col), _p(values), _p(rows), n, _p(q_rp), _p(q_col),
+                                          _p(q_val), _stream()), "csr_slice_rows")
+    return q_rp, q_col, q_val
+
+
+def col_sqsum(col_idx, values, n_cols, flat=False):
+    """Distinct columns (ascending) and normalised probabilities sum(v^2) (sqrt if flat) / total.
+    Returns (cand_cols int32[nnz], cand_prob f64[nnz], stats f64[3] on the device = {n_cand, total, n_positive})."""
+    _need_cuda(col_idx, values)
+    col = _index32(col_idx, "col_idx")
+    if values.dtype != torch.float64:
+        raise TypeError("col_sqsum: values must be float64")
+    values = values.contiguous()
+    nnz, dev = col.numel(), col.device
+    cand_cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    cand_prob = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)[:nnz]
+    stats = torch.empty(3, dtype=torch.float64, device=dev)
+    check(lib().dgllb_col_sqsum(_p(col), _p(values), nnz, int(n_cols), int(bool(flat)), _p(cand_cols), _p(cand_prob),
+                                _p(stats), _stream()), "col_sqsum")
+    return cand_cols, cand_prob, stats
+
+
+def weighted_choice(cand_cols, cand_prob, fanout, seed):
+    """Weighted draw without replacement, in drawing order.  Returns (sel int32[fanout], picks int64[fanout],
+    count int64[1] on the device)."""
+    _need_cuda(cand_cols, cand_prob)
+    if cand_prob.dtype != torch.float64:
+        raise TypeError("weighted_choice: probabilities must be float64")
+    cand_prob = cand_prob.contiguous()
+    cc = None if cand_cols is None else _index32(cand_cols, "cand_cols")
+    dev = cand_prob.device
+    fanout = int(fanout)
+    sel = torch.empty(max(fanout, 1), dtype=torch.int32, device=dev)[:fanout]
+    picks = torch.empty(max(fanout, 1), dtype=torch.int64, device=dev)[:fanout]
+    count = torch.empty(1, dtype=torch.int64, device=dev)
+    check(lib().dgllb_weighted_choice(_p(cc), _p(cand_prob), cand_prob.numel(), fanout,
+                                      ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _p(sel), _p(picks), _p(count),
+                                      _stream()), "weighted_choice")
+    return sel, picks, count
+
+
+def importance_scale(cand_prob, sel, count, n_total, mode):
+    """Column scales of the drawn candidates: ``mode='inverse'`` 1/p/count, ``mode='wrs'`` the WRS estimator."""
+    _need_cuda(cand_prob, sel, count)
+    sel = sel.contiguous()
+    if sel.dtype != torch.int32 or count.dtype != torch.int64 or cand_prob.dtype != torch.float64:
+        raise TypeError("importance_scale: sel int32, count int64, cand_prob float64 expected")
+    cap = sel.numel()
+    scale = torch.empty(max(cap, 1), dtype=torch.float64, device=sel.device)[:cap]
+    check(lib().dgllb_importance_scale(_p(cand_prob.contiguous()), _p(sel), _p(count), cap, int(n_total),
+                                       {"inverse": 0, "wrs": 1}[mode], _p(scale), _stream()), "importance_scale")
+    return scale
+
+
+def scatter_pos(pos, picks, count=None, reset=False):
+    """pos[picks[k]] = k (or -1 when ``reset``) for k < count; in place."""
+    _need_cuda(pos, picks, count)
+    if pos.dtype != torch.int32 or not pos.is_contiguous():
+        raise TypeError("scatter_pos: pos must be a contiguous int32 tensor")
+    picks = picks.to(torch.int64).contiguous()
+    check(lib().dgllb_scatter_pos(_p(pos), _p(picks), _p(count), picks.numel(), int(bool(reset)), _stream()),
+          "scatter_pos")
+    return pos
+
+
+def csr_select_cols(q_row_ptr, q_col, q_values, pos, scale=None, with_values=True):
+    """adj = Q[:, picks] * scale with columns relabelled through ``pos`` and rows sorted by the new label.
+    Returns (row_ptr int64[n+1], col int32[cap], values f64[cap] | None); the true nnz is row_ptr[-1] (device)."""
+    _need_cuda(q_row_ptr, q_col, q_values, pos, scale)
+    if q_row_ptr.dtype != torch.int64:
+        raise TypeError("csr_select_cols: q_row_ptr must be int64 (output of csr_slice_rows)")
+    q_rp = q_row_ptr.contiguous()
+    q_col = _index32(q_col, "q_col")
+    n, cap, dev = q_rp.numel() - 1, q_col.numel(), q_col.device
+    out_rp = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    out_col = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)[:cap]
+    out_val = torch.empty(max(cap, 1), dtype=torch.float64, device=dev)[:cap] if with_values else None
+    check(lib().dgllb_csr_select_cols(_p(q_rp), _p(q_col), _p(q_values), n, cap, _p(pos), _p(scale), _p(out_rp),
+                                      _p(out_col), _p(out_val), _stream()), "csr_select_cols")
+    return out_rp, out_col, out_val
+
+
 def gcn_fused_forward_v2(row_ptr, col_idx, values, X, W, num_neighbors, actual_F):
     _need_cuda(row_ptr, col_idx, values, X, W, num_neighbors)
     N, Fp, Hd = X.size(0), X.size(1), W.size(1)

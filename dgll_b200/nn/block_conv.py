@@ -56,7 +56,10 @@ class GraphConv(F.nn.Module):
         if self.bias is not None:
             F.init.zeros_(self.bias)
 
-    def forward(self, block, feat):
+    def forward(self, block, feat, edge_weight=None):
+        """``edge_weight`` (DGL's keyword): per-edge scalars multiplied into the messages; the degree normalisation
+        stays that of the unweighted block.  The layer-wise samplers leave their importance weights on
+        ``block.edge_weight``; like the reference's scripts the layer ignores them unless they are passed here."""
         feat_src = feat[0] if isinstance(feat, tuple) else feat
         g = _graph_of(block)
         n_dst = block.num_dst_nodes()
@@ -67,7 +70,8 @@ class GraphConv(F.nn.Module):
         w_first = self.weight is not None and self._in_feats > self._out_feats
         if w_first:
             feat_src = ops.linear(feat_src, self.weight)
-        rst = ops.spmm(g, feat_src, reduce="sum")
+        rst = ops.spmm(g if edge_weight is None else g.with_values(edge_weight.to(torch.float32)), feat_src,
+                       reduce="sum")
         if self._norm in ("right", "both"):
             in_deg = g.degrees().clamp(min=1)
             rst = rst * (in_deg.pow(-0.5) if self._norm == "both" else 1.0 / in_deg)[:, None]

@@ -338,6 +338,59 @@ int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const int32_t* row_
                       const int32_t* nbr_global, int64_t nnz_cap, int64_t* src_ids, int32_t* col_local,
                       int32_t* counts_out, void* stream);
 
+/* ------------------------------------------- layer-wise importance sampling -- */
+
+/*
+ * FastGCN / LADIES ("flat", "WRS" switches) on the device, replacing the scipy pipeline of
+ * GPU Accelerator/MQLadies.py:74-89, MQFastGCN.py:72-88, MQFastGCNFlatWrs.py:76-101 and utils.py:199-213.
+ * The Laplacian is a CSR with int32 columns and fp64 values (scipy's dtype).  Capacity convention: arrays sized by an
+ * upper bound, true counts written to device memory, so one layer needs two small read-backs.
+ *
+ * dgllb_csr_slice_rows_ptr / _fill:  Q = M[rows, :]   (out_row_ptr int64[n_rows+1]; read out_row_ptr[n_rows] = nnz(Q)
+ *   before allocating out_col / out_values; values may be NULL).
+ */
+int dgllb_csr_slice_rows_ptr(const void* row_ptr, int row_ptr_is64, const int64_t* rows, int64_t n_rows,
+                             int64_t* out_row_ptr, void* stream);
+int dgllb_csr_slice_rows_fill(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx, const double* values,
+                              const int64_t* rows, int64_t n_rows, const int64_t* out_row_ptr, int32_t* out_col,
+                              double* out_values, void* stream);
+/*
+ * Candidate columns and their probabilities: for every distinct column c of the nnz entries,
+ *   prob_i[c] = sum of values^2 (sqrt of it if flat), accumulated in stored order, products and sums rounded
+ *   separately (bit-identical to sum(Q.multiply(Q), axis=0)); prob = prob_i / sum(prob_i).
+ * cand_cols int32[nnz] / cand_prob double[nnz]: the first n_cand entries are the distinct columns in ascending order
+ * and their normalised probabilities, the rest -1 / 0.  stats double[3] (device) = {n_cand, sum(prob_i), #(prob_i > 0)}.
+ */
+int dgllb_col_sqsum(const int32_t* col_idx, const double* values, int64_t nnz, int64_t n_cols, int flat,
+                    int32_t* cand_cols, double* cand_prob, double* stats, void* stream);
+/*
+ * Draw min(fanout, #(prob > 0)) candidates without replacement with probabilities cand_prob, in drawing order
+ * (exponential keys -log(u)/p, smallest first; u from a counter-based generator keyed by (seed, node id)).
+ * cand_cols NULL = candidate i is node i.  sel int32[fanout] = candidate indices, picks int64[fanout] = node ids
+ * (-1 beyond the count), count int64[1] (device) = number drawn.  Same distribution as
+ * np.random.choice(n, s_num, p=prob, replace=False) (utils.py:201, MQFastGCN.py:80), not the same stream.
+ */
+int dgllb_weighted_choice(const int32_t* cand_cols, const double* cand_prob, int64_t n_cand, int fanout,
+                          uint64_t seed, int32_t* sel, int64_t* picks, int64_t* count, void* stream);
+/*
+ * Column scales for the drawn candidates sel[0..count): mode 0 = 1/p/count (MQFastGCN.py:82), mode 1 = the WRS
+ * estimator (utils.py:199-213, same operations in the same order, n_total = len(p) there).  scale double[cap],
+ * zero beyond count.
+ */
+int dgllb_importance_scale(const double* cand_prob, const int32_t* sel, const int64_t* count, int cap,
+                           int64_t n_total, int mode, double* scale, void* stream);
+/* pos[picks[k]] = k for k < min(cap, *count) (count NULL = cap), or -1 when reset != 0; picks < 0 skipped. */
+int dgllb_scatter_pos(int32_t* pos, const int64_t* picks, const int64_t* count, int64_t cap, int reset, void* stream);
+/*
+ * adj = Q[:, picks].multiply(scale).tocsr():  keeps the entries whose column c has pos[c] >= 0, relabels them to
+ * pos[c], scales by scale[pos[c]] (NULL = 1), rows sorted by the new label.  nnz_cap = allocated length of q_col /
+ * out_col / out_values (nnz(Q) is read from q_row_ptr[n_rows] on the device); out_row_ptr[n_rows] = nnz(adj).
+ * q_values / out_values may be NULL (topology only: what create_block receives at MQLadies.py:85).
+ */
+int dgllb_csr_select_cols(const int64_t* q_row_ptr, const int32_t* q_col, const double* q_values, int64_t n_rows,
+                          int64_t nnz_cap, const int32_t* pos, const double* scale, int64_t* out_row_ptr,
+                          int32_t* out_col, double* out_values, void* stream);
+
 /* ------------------------------------------------------------ legacy ABI -- */
 
 /*
