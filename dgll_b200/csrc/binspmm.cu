@@ -13,6 +13,7 @@
 // (18.6 MB) is L2 resident, so the kernel is bound by instruction issue / L2, not by HBM.
 // Algorithmic bytes: nnz*(4 + 4*ceil(F/32)) + n_dst*(4*F + r).
 #include "common.cuh"
+#include <stdlib.h>
 #include "internal.cuh"
 
 namespace dgllb {
@@ -250,17 +251,22 @@ extern "C" int dgllb_bin_spmm_csr(const void* row_ptr, int row_ptr_is64, const i
             plan->heavy_rows, plan->n_heavy_rows, static_cast<uint32_t*>(out), ldo, F);
         DGLLB_LAUNCH_CHECK();
     }
-    const long long blocks = (n_dst * 32 + 255) / 256;
-    const long long hblocks = heavy ? (plan->n_items * 32 + 255) / 256 : 0;
+    int tb = 64;  // small blocks retire evenly on ragged rows (4.54 -> 4.26 ms, Reddit-shaped)
+    if (const char* e = getenv("DGLLB_BIN_TB")) {
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128 || v == 256) tb = v;
+    }
+    const long long blocks = (n_dst * 32 + tb - 1) / tb;
+    const long long hblocks = heavy ? (plan->n_items * 32 + tb - 1) / tb : 0;
     DGLLB_REQUIRE(blocks < (1ll << 31) && hblocks < (1ll << 31), "bin_spmm: grid too large");
     const unsigned g = static_cast<unsigned>(blocks), hg = static_cast<unsigned>(hblocks);
 #define DGLLB_BIN_CASE(NW)                                                                                   \
     case NW:                                                                                                 \
         if (heavy)                                                                                           \
-            bin_spmm_kernel<NW, true><<<hg, 256, 0, st>>>(row_ptr, row_ptr_is64, col_idx, packed,            \
+            bin_spmm_kernel<NW, true><<<hg, tb, 0, st>>> (row_ptr, row_ptr_is64, col_idx, packed,            \
                                                           words_per_row, out, ldo, n_dst, F, out_mode,      \
                                                           chunk, plan->items, plan->n_items);               \
-        bin_spmm_kernel<NW, false><<<g, 256, 0, st>>>(row_ptr, row_ptr_is64, col_idx, packed, words_per_row, \
+        bin_spmm_kernel<NW, false><<<g, tb, 0, st>>> (row_ptr, row_ptr_is64, col_idx, packed, words_per_row, \
                                                       out, ldo, n_dst, F, out_mode, chunk, nullptr, 0);      \
         break;
     switch (nw4) {

@@ -219,13 +219,13 @@ constexpr int kRowWarps = 8;
 // HEAVY = true : warp w owns plan item w = (row, k): edges [k*chunk, (k+1)*chunk) of a long row; it writes its partial
 //                online-softmax state (unnormalised acc, running max m, running sum l) to p.ws and
 //                gat_combine_heavy_kernel merges the chunks of a row (exact log-sum-exp merge, no atomics).
-template <int NV, bool HEAVY>
-__global__ void __launch_bounds__(kRowWarps * 32)
+template <int NV, bool HEAVY, int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 gat_forward_row_kernel(const GatParams p) {
-    __shared__ int s_c[kRowWarps][32];
-    __shared__ float s_p[kRowWarps][32][4];
+    __shared__ int s_c[WARPS][32];
+    __shared__ float s_p[WARPS][32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wid = static_cast<long long>(blockIdx.x) * kRowWarps + warp;
+    const long long wid = static_cast<long long>(blockIdx.x) * WARPS + warp;
     const int H = p.heads, FD = p.heads * p.D;
     long long row, beg, end;
     if (HEAVY) {
@@ -312,11 +312,11 @@ gat_forward_row_kernel(const GatParams p) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) acc[i][a] *= cr;
         }
-        for (int k = 0; k < n; k += 4) {
-            float4 raw[4][NV];
-            float w[4][NV];
+        for (int k = 0; k < n; k += U) {
+            float4 raw[U][NV];
+            float w[U][NV];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const bool on = k + u < n;
                 const int c = s_c[warp][(k + u) & 31];
                 const float* src = p.Wh + static_cast<long long>(c) * p.ldw + lane * 4;
@@ -332,7 +332,7 @@ gat_forward_row_kernel(const GatParams p) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     acc[i][0] = fmaf(w[u][i], raw[u][i].x, acc[i][0]);
@@ -483,7 +483,7 @@ template <int VE, int LANES, int NCH, bool HEAVY>
 __global__ void __launch_bounds__(kGatThreads)
 gat_backward_edge_kernel(const GatBwdParams p) {
     const int lig = threadIdx.x & (LANES - 1);
-    const long long group = (static_cast<long long>(blockIdx.x) * kGatThreads + threadIdx.x) / LANES;
+    const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                          : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
     const long long unit = group / p.heads;       // dst row, or plan item (row, chunk) when HEAVY
@@ -595,7 +595,7 @@ template <int VE, int LANES, bool HEAVY>
 __global__ void __launch_bounds__(kGatThreads)
 gat_backward_node_kernel(const GatBwdParams p, int n_slabs) {
     const int lig = threadIdx.x & (LANES - 1);
-    const long long group = (static_cast<long long>(blockIdx.x) * kGatThreads + threadIdx.x) / LANES;
+    const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                          : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
     const int per_row = p.heads * n_slabs;
@@ -718,17 +718,24 @@ __global__ void gat_bwd_combine_node_kernel(const GatBwdParams p) {
     }
 }
 
+static int gat_bwd_block_threads() {
+    int tb = 64;  // small blocks retire evenly on ragged rows: 64.0 -> 55.9 ms (products-shaped)
+    if (const char* e = getenv("DGLLB_GAT_BWD_TB")) tb = atoi(e);
+    return (tb == 32 || tb == 64 || tb == 128 || tb == 256) ? tb : 64;
+}
+
 template <int VE, int LANES, bool HEAVY>
 static int launch_gat_bwd_edge(const GatBwdParams& p, int nch, cudaStream_t st) {
     const long long groups = (HEAVY ? p.e_n_items : p.n_dst) * p.heads;
     if (groups == 0) return DGLLB_OK;
-    const int gpb = kGatThreads / LANES;
+    const int tb = gat_bwd_block_threads();
+    const int gpb = tb / LANES;
     const long long blocks = (groups + gpb - 1) / gpb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
     const unsigned g = static_cast<unsigned>(blocks);
-    if (nch <= 1) gat_backward_edge_kernel<VE, LANES, 1, HEAVY><<<g, kGatThreads, 0, st>>>(p);
-    else if (nch <= 2) gat_backward_edge_kernel<VE, LANES, 2, HEAVY><<<g, kGatThreads, 0, st>>>(p);
-    else if (nch <= 4) gat_backward_edge_kernel<VE, LANES, 4, HEAVY><<<g, kGatThreads, 0, st>>>(p);
+    if (nch <= 1) gat_backward_edge_kernel<VE, LANES, 1, HEAVY><<<g, tb, 0, st>>>(p);
+    else if (nch <= 2) gat_backward_edge_kernel<VE, LANES, 2, HEAVY><<<g, tb, 0, st>>>(p);
+    else if (nch <= 4) gat_backward_edge_kernel<VE, LANES, 4, HEAVY><<<g, tb, 0, st>>>(p);
     else {
         set_error("gat_backward: head width D=%d too large for this build", p.D);
         return DGLLB_ERR_UNSUPPORTED;
@@ -741,10 +748,11 @@ template <int VE, int LANES, bool HEAVY>
 static int launch_gat_bwd_node(const GatBwdParams& p, int nch, cudaStream_t st) {
     const long long groups = (HEAVY ? p.t_n_items : p.n_src) * p.heads * nch;
     if (groups == 0) return DGLLB_OK;
-    const int gpb = kGatThreads / LANES;
+    const int tb = gat_bwd_block_threads();
+    const int gpb = tb / LANES;
     const long long blocks = (groups + gpb - 1) / gpb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "gat_backward: grid too large");
-    gat_backward_node_kernel<VE, LANES, HEAVY><<<static_cast<unsigned>(blocks), kGatThreads, 0, st>>>(p, nch);
+    gat_backward_node_kernel<VE, LANES, HEAVY><<<static_cast<unsigned>(blocks), tb, 0, st>>>(p, nch);
     DGLLB_LAUNCH_CHECK();
     return DGLLB_OK;
 }
@@ -826,18 +834,29 @@ static int launch_gat_fwd(GatParams& p, const dgllb_csr_plan* plan, cudaStream_t
             DGLLB_CUDA_TRY(cudaMallocAsync(&ws, sizeof(float) * static_cast<size_t>(p.n_items) * (FD + 8), st));
         }
         p.ws = ws;
-        const long long blocks = (p.n_dst + kRowWarps - 1) / kRowWarps;
-        const long long hblocks = (p.n_items + kRowWarps - 1) / kRowWarps;
+        // one warp per block: with 8 warps a block kept its registers until its longest row was done (achieved
+        // occupancy 27 %, profiles/r01_gat_fwd_bwd.txt); 4 edges in flight per warp (8 spills)
+        int cw = 1;  // DGLLB_GAT_ROW_WARPS=1|4|8 pins the block size (measurement aid)
+        if (const char* cfg = getenv("DGLLB_GAT_ROW_WARPS")) cw = atoi(cfg);
+        const long long blocks = (p.n_dst + cw - 1) / cw;
+        const long long hblocks = (p.n_items + cw - 1) / cw;
         DGLLB_REQUIRE(blocks < (1ll << 31) && hblocks < (1ll << 31), "gat_forward: grid too large");
         const unsigned g = static_cast<unsigned>(blocks), hg = static_cast<unsigned>(hblocks);
+#define DGLLB_GAT_ROW3(NVV, UU, WW)                                                               \
+        do {                                                                                      \
+            if (heavy) gat_forward_row_kernel<NVV, true, UU, WW><<<hg, WW * 32, 0, st>>>(p);      \
+            gat_forward_row_kernel<NVV, false, UU, WW><<<g, WW * 32, 0, st>>>(p);                 \
+        } while (0)
 #define DGLLB_GAT_ROW(NVV)                                                                        \
         do {                                                                                      \
-            if (heavy) gat_forward_row_kernel<NVV, true><<<hg, kRowWarps * 32, 0, st>>>(p);       \
-            gat_forward_row_kernel<NVV, false><<<g, kRowWarps * 32, 0, st>>>(p);                  \
+            if (cw == 8) DGLLB_GAT_ROW3(NVV, 4, 8);                                               \
+            else if (cw == 4) DGLLB_GAT_ROW3(NVV, 4, 4);                                          \
+            else DGLLB_GAT_ROW3(NVV, 4, 1);                                                       \
         } while (0)
         if (FD <= 128) DGLLB_GAT_ROW(1);
         else if (FD <= 256) DGLLB_GAT_ROW(2);
         else DGLLB_GAT_ROW(4);
+#undef DGLLB_GAT_ROW3
 #undef DGLLB_GAT_ROW
         g_launch_count.fetch_add(heavy ? 1 : 0);
         DGLLB_LAUNCH_CHECK();

@@ -126,7 +126,7 @@ spmm_rowslab_kernel(const SpmmParams p) {
     typedef RowLoad<XT, VE> L;
     constexpr int A = L::kAcc;
     const int lig = threadIdx.x & (LANES - 1);                 // lane in group
-    const long long group = (static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x) / LANES;
+    const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu
                                          : (((1u << LANES) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
 
@@ -564,13 +564,20 @@ template <typename XT, int VE, int LANES>
 static int launch_spmm(const SpmmParams& p, bool is_max, cudaStream_t st) {
     const long long groups = (p.n_heavy_items + p.n_dst) * p.n_slabs;
     if (groups == 0) return DGLLB_OK;
-    const int gpb = kThreads / LANES;
+    // 64-thread blocks: a block's registers are held until its slowest row finishes, so small blocks retire evenly on
+    // ragged rows (headline block 0.127 -> 0.115 ms per step, full graphs 8 % faster at F=256; profiles/r01_block_size.md)
+    int tb = 64;
+    if (const char* e = getenv("DGLLB_SPMM_TB")) {
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128 || v == 256) tb = v;
+    }
+    const int gpb = tb / LANES;
     const long long blocks = (groups + gpb - 1) / gpb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "spmm: grid too large (%lld blocks)", blocks);
     if (is_max)
-        spmm_rowslab_kernel<XT, VE, LANES, true><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
+        spmm_rowslab_kernel<XT, VE, LANES, true><<<static_cast<unsigned>(blocks), tb, 0, st>>>(p);
     else
-        spmm_rowslab_kernel<XT, VE, LANES, false><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(p);
+        spmm_rowslab_kernel<XT, VE, LANES, false><<<static_cast<unsigned>(blocks), tb, 0, st>>>(p);
     DGLLB_LAUNCH_CHECK();
     return DGLLB_OK;
 }

@@ -90,15 +90,15 @@ class CsrGraph:
                 self._bin_plan = K.CsrPlan(self.row_ptr, chunk_edges=1024)
         return self._bin_plan
 
-    def gat_bwd_plan(self):
-        """nnz-split for the GAT backward passes (256-edge items: 64.0 ms vs 69.6 ms at 1,024 and 96.3 ms unsplit on
-        the products-shaped graph, profiles/r01_kernels.jsonl)."""
-        if getattr(self, "_gat_bwd_plan", False) is False:
-            self._gat_bwd_plan = None
+    def gat_plan(self):
+        """nnz-split for the fused GAT kernels, forward and both backward passes (256-edge items: forward 20.9 ms vs
+        23.7 ms at 1,024; backward 55.9 ms vs 96.3 ms unsplit on the products-shaped graph, profiles/r01_kernels.jsonl)."""
+        if getattr(self, "_gat_plan", False) is False:
+            self._gat_plan = None
             if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
                     float(self.degrees().max().item()) > 256:
-                self._gat_bwd_plan = K.CsrPlan(self.row_ptr, chunk_edges=256)
-        return self._gat_bwd_plan
+                self._gat_plan = K.CsrPlan(self.row_ptr, chunk_edges=256)
+        return self._gat_plan
 
     def transpose(self):
         """CsrGraph of A^T (values carried along); ``perm[e_T] = e`` kept for per-edge gradients."""
@@ -298,7 +298,7 @@ class _GatFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wh, el, er, graph, heads, slope, mode, dropout, seed):
         out, rmax, rsum = K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode,
-                                        save_stats=True, n_dst=graph.n_dst, plan=graph.bin_plan(), dropout=dropout,
+                                        save_stats=True, n_dst=graph.n_dst, plan=graph.gat_plan(), dropout=dropout,
                                         seed=seed)
         ctx.graph, ctx.heads, ctx.slope, ctx.mode = graph, heads, slope, mode
         ctx.dropout, ctx.seed = dropout, seed
@@ -312,8 +312,8 @@ class _GatFn(torch.autograd.Function):
         gt = graph.transpose()
         d_wh, d_el, d_er = K.gat_backward(graph.row_ptr, graph.col, gt.row_ptr, gt.col, graph._perm, wh, el, er, out,
                                           rmax, rsum, grad.contiguous(), ctx.heads, ctx.slope, mode=ctx.mode,
-                                          dropout=ctx.dropout, seed=ctx.seed, plan=graph.gat_bwd_plan(),
-                                          t_plan=gt.gat_bwd_plan())
+                                          dropout=ctx.dropout, seed=ctx.seed, plan=graph.gat_plan(),
+                                          t_plan=gt.gat_plan())
         return d_wh, d_el, d_er, None, None, None, None, None, None
 
 
@@ -334,7 +334,7 @@ def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False
         out = _GatFn.apply(wh, el, er, graph, heads, slope, mode, float(dropout), seed)
         return torch.nn.functional.elu(out) if elu else out
     return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst,
-                         plan=graph.bin_plan(), dropout=float(dropout), seed=seed)
+                         plan=graph.gat_plan(), dropout=float(dropout), seed=seed)
 
 
 # -------------------------------------------------------------- binarized ---

@@ -176,6 +176,13 @@ def main():
         ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out, plan=gplan), args.iters)
         report("gat_forward[row + plan 1024]", "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes,
                {"heavy_rows": gplan.n_heavy_rows, "chunks": gplan.n_chunks})
+        gplan256 = K.CsrPlan(rp, chunk_edges=256)
+        for warps in ("8", "4", "1"):
+            os.environ["DGLLB_GAT_ROW_WARPS"] = warps
+            ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out, plan=gplan256), args.iters)
+            report("gat_forward[row + plan 256, %s warp(s) per block]" % warps, "products-shaped", ms, nbytes,
+                   {"heavy_rows": gplan256.n_heavy_rows, "chunks": gplan256.n_chunks})
+        os.environ.pop("DGLLB_GAT_ROW_WARPS", None)
         ms = timeit(lambda: K.spmm_csr(rp, col, wh, reduce="sum", out=out), args.iters)
         report("spmm_full_graph (same graph, F=256)", "products-shaped", ms, nnz * (4 + 256 * 4) + Np * (256 * 4 + 8))
         # backward: pass 1 over the CSR (alpha, dz per edge), pass 2 over the transposed CSR (d_Wh, d_er)
