@@ -82,7 +82,8 @@ class CsrGraph:
         return self._plan
 
     def bin_plan(self):
-        """nnz-split for the binarized kernel (one warp per 1,024 edges of a long row; integer atomics, exact)."""
+        """nnz-split into 1,024-edge items: the binarized kernel (integer atomics, exact) and the fused GAT forward
+        (partial softmax states merged exactly)."""
         if getattr(self, "_bin_plan", False) is False:
             self._bin_plan = None
             if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
@@ -91,8 +92,9 @@ class CsrGraph:
         return self._bin_plan
 
     def gat_plan(self):
-        """nnz-split for the fused GAT kernels, forward and both backward passes (256-edge items: forward 20.9 ms vs
-        23.7 ms at 1,024; backward 55.9 ms vs 96.3 ms unsplit on the products-shaped graph, profiles/r01_kernels.jsonl)."""
+        """nnz-split for the two GAT backward passes (256-edge items: 55.5 ms vs 57.5 ms at 1,024 and 84.1 ms unsplit on
+        the products-shaped graph; the forward is best with the 1,024-edge ``bin_plan``: 19.7 ms vs 20.9 ms —
+        profiles/r01_kernels.jsonl)."""
         if getattr(self, "_gat_plan", False) is False:
             self._gat_plan = None
             if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
@@ -298,7 +300,7 @@ class _GatFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wh, el, er, graph, heads, slope, mode, dropout, seed):
         out, rmax, rsum = K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode,
-                                        save_stats=True, n_dst=graph.n_dst, plan=graph.gat_plan(), dropout=dropout,
+                                        save_stats=True, n_dst=graph.n_dst, plan=graph.bin_plan(), dropout=dropout,
                                         seed=seed)
         ctx.graph, ctx.heads, ctx.slope, ctx.mode = graph, heads, slope, mode
         ctx.dropout, ctx.seed = dropout, seed
@@ -334,7 +336,7 @@ def gat_aggregate(adj, wh, el, er, heads=1, slope=0.2, mode="softmax", elu=False
         out = _GatFn.apply(wh, el, er, graph, heads, slope, mode, float(dropout), seed)
         return torch.nn.functional.elu(out) if elu else out
     return K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst,
-                         plan=graph.gat_plan(), dropout=float(dropout), seed=seed)
+                         plan=graph.bin_plan(), dropout=float(dropout), seed=seed)
 
 
 # -------------------------------------------------------------- binarized ---
