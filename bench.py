@@ -446,7 +446,7 @@ def main():
         torch.manual_seed(args.seed)
         labels = torch.randint(0, 41, (N_NODES,), device=dev, generator=gen)
         model = dnn.GraphSAGE(FEAT, HIDDEN, 41, 2, torch.relu, 0.0).to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=0.003)
+        opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
         perm_e = torch.randperm(n_train, device=dev, generator=torch.Generator(device=dev).manual_seed(args.seed))
         shard = perm_e[rank::world].contiguous()              # use_ddp-style split of the shuffled train seeds
         res = {}
@@ -459,13 +459,32 @@ def main():
             pre = T.make_batches(row_ptr, col_idx, shard, FANOUTS, BATCH, rng_seed=3)
             barrier()
             r_pre = T.sage_epoch(model, opt, table, labels, FEAT, batches=pre, precision=prec)
+            # the same step captured once as a CUDA graph on fixed-capacity block buffers (train.GraphedSageTrainer):
+            # (a) pre-sampled blocks, (b) device sampler + block builder run eagerly, training step replayed
+            g_pre = g_loop = float("nan")
+            g_err = None
+            try:
+                opt_g = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=True)
+                tr = T.GraphedSageTrainer(model, opt_g, table, labels, BATCH, FANOUTS, precision=prec)
+                tr.load(*pre[0])
+                tr.capture()
+                barrier()
+                g_pre = tr.epoch(pre)["time_s"]
+                barrier()
+                g_loop = tr.epoch(T.iter_batches(row_ptr, col_idx, shard, FANOUTS, BATCH, rng_seed=4))["time_s"]
+                del tr, opt_g
+            except Exception as ex:                                  # report, keep the eager numbers
+                g_err = "%s: %s" % (type(ex).__name__, str(ex)[:200])
             del pre
-            t = torch.tensor([r_e2e["time_s"], r_pre["time_s"]], device=dev, dtype=torch.float64)
+            t = torch.tensor([r_e2e["time_s"], r_pre["time_s"], g_pre, g_loop], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res[prec] = {"epoch_s_sampler_in_loop": round(t[0].item(), 4), "epoch_s_presampled": round(t[1].item(), 4),
-
+                         "epoch_s_presampled_cuda_graph": round(t[2].item(), 4),
+                         "epoch_s_sampler_in_loop_cuda_graph": round(t[3].item(), 4),
                          "batches_per_gpu": r_e2e["n_batches"], "loss": round(r_e2e["loss"], 4)}
+            if g_err:
+                res[prec]["cuda_graph_error"] = g_err
         epoch = {"model": "GraphSAGE-mean 2-layer 602-256-41, fanout 25/10, batch 1024/GPU, Adam, fwd+bwd+step",
                  "train_seeds": int(perm.numel()), "gemm": res}
 

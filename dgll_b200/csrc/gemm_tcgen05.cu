@@ -29,36 +29,70 @@ constexpr int kTmemCols = 128;
 
 // ------------------------------------------------------------------ pre-pass --
 // dst[r, k] (bf16, row stride Kp) = TR ? src[k, r] : src[r, k];  zero for k >= K.  32x32 tiles through shared memory.
-template <bool TR>
-__global__ void __launch_bounds__(256)
-pack_bf16_kernel(const float* __restrict__ src, long long ld, __nv_bfloat16* __restrict__ dst, long long rows, int K,
-                 int Kp) {
-    __shared__ float tile[32][33];
+struct PackOperand {
+    const float* src;
+    long long ld, rows;
+    __nv_bfloat16* dst;
+    int transposed;      // 1: src is [K, rows] (read src[k, r]); 0: src is [rows, K]
+    unsigned blocks_x;   // ceil(rows / 32)
+};
+
+__device__ __forceinline__ void pack_tile(const PackOperand& o, unsigned bx, unsigned by, int K, int Kp,
+                                          float (*tile)[33]) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const long long r0 = static_cast<long long>(blockIdx.x) * 32;
-    const int k0 = blockIdx.y * 32;
-    if (TR) {
+    const long long r0 = static_cast<long long>(bx) * 32;
+    const int k0 = by * 32;
+    if (o.transposed) {
         // read src[k0+j, r0+tx] coalesced along r, write dst[r0+j', k0+tx] coalesced along k
         for (int j = ty; j < 32; j += 8) {
             const int k = k0 + j;
             const long long r = r0 + tx;
-            tile[j][tx] = (k < K && r < rows) ? __ldg(src + static_cast<long long>(k) * ld + r) : 0.f;
+            tile[j][tx] = (k < K && r < o.rows) ? __ldg(o.src + static_cast<long long>(k) * o.ld + r) : 0.f;
         }
         __syncthreads();
         for (int j = ty; j < 32; j += 8) {
             const long long r = r0 + j;
             const int k = k0 + tx;
-            if (r < rows && k < Kp) dst[r * Kp + k] = __float2bfloat16(tile[tx][j]);
+            if (r < o.rows && k < Kp) o.dst[r * Kp + k] = __float2bfloat16(tile[tx][j]);
         }
     } else {
         for (int j = ty; j < 32; j += 8) {
             const long long r = r0 + j;
             const int k = k0 + tx;
-            if (r < rows && k < Kp) {
-                const float v = k < K ? __ldg(src + r * ld + k) : 0.f;
-                dst[r * Kp + k] = __float2bfloat16(v);
+            if (r < o.rows && k < Kp) {
+                const float v = k < K ? __ldg(o.src + r * o.ld + k) : 0.f;
+                o.dst[r * Kp + k] = __float2bfloat16(v);
             }
         }
+    }
+}
+
+// BOTH operands in one launch: blocks [0, a.blocks_x) of the x dimension pack A, the rest pack B (the small GEMMs of a
+// training step are launch-latency bound: 4.5 us per pack launch against ~1 us of work).
+// dst[r, k] (bf16, row stride Kp) = transposed ? src[k, r] : src[r, k];  zero for k >= K.  32x32 tiles through smem.
+__global__ void __launch_bounds__(256)
+pack_bf16_kernel(const PackOperand a, const PackOperand b, int K, int Kp) {
+    __shared__ float tile[32][33];
+    if (blockIdx.x < a.blocks_x) pack_tile(a, blockIdx.x, blockIdx.y, K, Kp, tile);
+    else pack_tile(b, blockIdx.x - a.blocks_x, blockIdx.y, K, Kp, tile);
+}
+
+// split-K: out = (accumulate ? out : 0) + sum_z partial[z] (fixed order: deterministic) + bias, then the epilogue
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, long long slab, int splits, float* __restrict__ C, long long ldc,
+                     long long M, int N, int ldp, const float* __restrict__ bias, int epi, int accumulate) {
+    const long long total = M * N;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / N;
+        const int c = static_cast<int>(i - r * N);
+        float v = accumulate ? C[r * ldc + c] : 0.f;
+        const float* p = part + r * ldp + c;
+        for (int z = 0; z < splits; ++z) v += p[z * slab];
+        if (bias) v += __ldg(bias + c);
+        if (epi & DGLLB_EPI_RELU) v = fmaxf(v, 0.f);
+        if (epi & DGLLB_EPI_ELU) v = v > 0.f ? v : expm1f(v);
+        C[r * ldc + c] = v;
     }
 }
 
@@ -129,8 +163,8 @@ __device__ __forceinline__ float gemm_epi(float v, int epi) {
 // ------------------------------------------------------------------ kernel ---
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    float* __restrict__ C, long long ldc, long long M, int N, int num_kb,
-                    const float* __restrict__ bias, int epi, int accumulate) {
+                    float* __restrict__ C, long long ldc, long long M, int N, int num_kb_total, int kb_per_split,
+                    long long split_slab, const float* __restrict__ bias, int epi, int accumulate) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atom
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -141,6 +175,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+    // split-K: this CTA reduces k-blocks [kb0, kb0 + num_kb) into its own slab of the partial buffer
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int num_kb = min(kb_per_split, num_kb_total - kb0);
+    C += static_cast<long long>(blockIdx.z) * split_slab;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -167,8 +205,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t ph = (kb / kStages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
-                tma_load_2d(smem_a + s * kStageBytesA, &tmap_a, kb * kBK, m0, &full_bar[s]);
-                tma_load_2d(smem_b + s * kStageBytesB, &tmap_b, kb * kBK, n0, &full_bar[s]);
+                tma_load_2d(smem_a + s * kStageBytesA, &tmap_a, (kb0 + kb) * kBK, m0, &full_bar[s]);
+                tma_load_2d(smem_b + s * kStageBytesB, &tmap_b, (kb0 + kb) * kBK, n0, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
@@ -291,7 +329,8 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
         // degenerate / oversized: the SIMT path handles it exactly
         return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epi, accumulate, st);
     }
-    { DevInfo di_; int rc_ = get_devinfo(&di_); if (rc_ != DGLLB_OK) return rc_; }  // also configures the workspace pool
+    DevInfo di;
+    { int rc_ = get_devinfo(&di); if (rc_ != DGLLB_OK) return rc_; }  // also configures the workspace pool
     const int Kp = static_cast<int>((K + kBK - 1) / kBK * kBK);
     const size_t bytes_a = (static_cast<size_t>(M) * Kp * 2 + 255) & ~static_cast<size_t>(255);
     const size_t bytes_b = (static_cast<size_t>(N) * Kp * 2 + 255) & ~static_cast<size_t>(255);
@@ -300,33 +339,70 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
     __nv_bfloat16* Ab = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* Bb = reinterpret_cast<__nv_bfloat16*>(ws + bytes_a);
     int rc = DGLLB_OK;
+    float* part = nullptr;
     do {
-        const dim3 ga(static_cast<unsigned>((M + 31) / 32), static_cast<unsigned>((Kp + 31) / 32));
-        const dim3 gb(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((Kp + 31) / 32));
-        if (ga.y > 65535u || gb.y > 65535u) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: K too large"); break; }
+        PackOperand pa, pb;
         // A operand: rows = M, K-major.  stored [M,K] -> direct; stored [K,M] (transA) -> transpose
-        if (transA) pack_bf16_kernel<true><<<ga, 256, 0, st>>>(A, lda, Ab, M, static_cast<int>(K), Kp);
-        else pack_bf16_kernel<false><<<ga, 256, 0, st>>>(A, lda, Ab, M, static_cast<int>(K), Kp);
-        g_launch_count.fetch_add(1);
+        pa.src = A; pa.ld = lda; pa.rows = M; pa.dst = Ab; pa.transposed = transA ? 1 : 0;
+        pa.blocks_x = static_cast<unsigned>((M + 31) / 32);
         // B operand: rows = N, K-major (= B^T).  stored [K,N] -> transpose; stored [N,K] (transB) -> direct
-        if (transB) pack_bf16_kernel<false><<<gb, 256, 0, st>>>(B, ldb, Bb, N, static_cast<int>(K), Kp);
-        else pack_bf16_kernel<true><<<gb, 256, 0, st>>>(B, ldb, Bb, N, static_cast<int>(K), Kp);
+        pb.src = B; pb.ld = ldb; pb.rows = N; pb.dst = Bb; pb.transposed = transB ? 0 : 1;
+        pb.blocks_x = static_cast<unsigned>((N + 31) / 32);
+        const dim3 gp(pa.blocks_x + pb.blocks_x, static_cast<unsigned>((Kp + 31) / 32));
+        if (gp.y > 65535u) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: K too large"); break; }
+        pack_bf16_kernel<<<gp, 256, 0, st>>>(pa, pb, static_cast<int>(K), Kp);
         g_launch_count.fetch_add(1);
         CUtensorMap ta, tb;
         if ((rc = make_tmap(&ta, Ab, M, Kp)) != DGLLB_OK) break;
         if ((rc = make_tmap(&tb, Bb, N, Kp)) != DGLLB_OK) break;
         const size_t smem = static_cast<size_t>(kStages) * (kStageBytesA + kStageBytesB) + 1024;
-        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
-        const dim3 grid(static_cast<unsigned>((M + kBM - 1) / kBM), static_cast<unsigned>((N + kBN - 1) / kBN));
+        static std::once_flag attr_once;
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(attr_once, [&]() {
+            attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem));
+        });
+        if (attr_err != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(attr_err)); rc = DGLLB_ERR_CUDA; break; }
+        dim3 grid(static_cast<unsigned>((M + kBM - 1) / kBM), static_cast<unsigned>((N + kBN - 1) / kBN), 1);
         if (grid.y > 65535u) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: N too large"); break; }
-        gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, st>>>(ta, tb, C, ldc, M, static_cast<int>(N), Kp / kBK, bias,
-                                                              epi, accumulate);
-        g_launch_count.fetch_add(1);
-        e = cudaGetLastError();
+        // split-K when the output has too few tiles to occupy the SMs and the reduction is long (dW = X^T G of a
+        // training step: 2 x 5 tiles, K = 11,264 -> 85 us on 10 SMs).  Partials go to a workspace and are summed in a
+        // fixed order by splitk_reduce_kernel: deterministic, unlike atomics.
+        const int num_kb = Kp / kBK;
+        const long long tiles = static_cast<long long>(grid.x) * grid.y;
+        int splits = 1, kb_per = num_kb;
+        if (tiles * 2 <= di.sm_count && num_kb >= 8) {
+            long long want = di.sm_count / tiles;
+            if (want > 32) want = 32;
+            if (want > num_kb / 4) want = num_kb / 4;
+            if (want >= 2) {
+                kb_per = static_cast<int>((num_kb + want - 1) / want);
+                splits = (num_kb + kb_per - 1) / kb_per;
+            }
+        }
+        if (splits > 1) {
+            const int ldp = static_cast<int>((N + 3) / 4 * 4);
+            const long long slab = M * ldp;
+            cudaError_t e = cudaMallocAsync(&part, sizeof(float) * static_cast<size_t>(slab) * splits, st);
+            if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
+            grid.z = static_cast<unsigned>(splits);
+            gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, st>>>(ta, tb, part, ldp, M, static_cast<int>(N), num_kb,
+                                                                  kb_per, slab, nullptr, 0, 0);
+            long long rb = (M * N + 255) / 256;
+            if (rb > static_cast<long long>(di.sm_count) * 8) rb = static_cast<long long>(di.sm_count) * 8;
+            splitk_reduce_kernel<<<static_cast<unsigned>(rb), 256, 0, st>>>(part, slab, splits, C, ldc, M,
+                                                                            static_cast<int>(N), ldp, bias, epi,
+                                                                            accumulate);
+            g_launch_count.fetch_add(2);
+        } else {
+            gemm_tcgen05_kernel<<<grid, kGemmThreads, smem, st>>>(ta, tb, C, ldc, M, static_cast<int>(N), num_kb,
+                                                                  num_kb, 0, bias, epi, accumulate);
+            g_launch_count.fetch_add(1);
+        }
+        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("gemm: launch failed: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
     } while (0);
+    if (part) cudaFreeAsync(part, st);
     cudaFreeAsync(ws, st);
     return rc;
 }

@@ -77,8 +77,10 @@ extern "C" int dgllb_csr_transpose(const void* row_ptr, int row_ptr_is64, const 
     }
     DGLLB_REQUIRE(col_idx && t_col_idx, "csr_transpose: null pointer");
     // workspace: rowid, eid, keys_out, eid_out (4 x nnz ints) + CUB temp
+    // keys 0..n_cols: a column id equal to n_cols is PADDING — it sorts behind every real column and lands in no row of
+    // the result (t_row_ptr[n_cols] = number of real entries), so fixed-capacity edge arrays can be transposed as they are
     int end_bit = 1;
-    while ((1ll << end_bit) < n_cols && end_bit < 32) ++end_bit;
+    while ((1ll << end_bit) <= n_cols && end_bit < 32) ++end_bit;
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<const int*>(nullptr),
                                     static_cast<int*>(nullptr), static_cast<const int*>(nullptr),

@@ -15,7 +15,16 @@ from ._lib import (BF16, EPI_ELU, EPI_RELU, F32, GAT_EXP_NEG, GAT_SOFTMAX, MAX, 
 _REDUCE = {"sum": SUM, "add": SUM, "mean": MEAN, "max": MAX}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    """The current torch stream of the current device as a raw ``cudaStream_t``.  Goes through torch's C entry points:
+    ``torch.cuda.current_stream()`` builds a Python Stream object per call (~18 us, 12 % of a training step's host
+    time in tools/profile_epoch.py)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return ctypes.c_void_p(_raw_stream(_raw_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

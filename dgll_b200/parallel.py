@@ -226,11 +226,8 @@ def allreduce_gradients(params, group=None, average=True):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+    views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
+    torch._foreach_copy_(grads, views)          # one multi-tensor launch instead of a copy per parameter
 
 
 def shard_seeds(seeds, n_nodes, rank, world):

@@ -21,6 +21,13 @@ def make_batches(row_ptr, col_idx, seeds, fanouts, batch_size, rng_seed=0):
     return out
 
 
+def iter_batches(row_ptr, col_idx, seeds, fanouts, batch_size, rng_seed=0):
+    """The sampler in the loop: yields (seeds, blocks) one mini-batch at a time (device sampler + block builder)."""
+    for b, i in enumerate(range(0, seeds.numel(), batch_size)):
+        s = seeds[i:i + batch_size]
+        yield s, G.sample_blocks(row_ptr, col_idx, s, fanouts, rng_seed=rng_seed * 7919 + b)
+
+
 def sage_epoch(model, opt, table, labels, n_feat, row_ptr=None, col_idx=None, seeds=None, fanouts=(25, 10),
                batch_size=1024, batches=None, rng_seed=0, group=None, precision=None):
     """One epoch.  ``batches`` (from ``make_batches``) = pre-sampled blocks; otherwise the sampler runs in the loop.
@@ -80,3 +87,150 @@ def sage_epoch_pipelined(model, opt, table, labels, row_ptr, col_idx, seeds, fan
     if precision is not None:
         ops.set_gemm_precision(prev)
     return res
+
+
+class GraphedSageTrainer:
+    """The training step of ``sage_epoch`` captured ONCE as a CUDA graph and replayed for every mini-batch.
+
+    Block shapes differ per mini-batch, so the step is captured on fixed-capacity buffers: ``batch_size`` seeds,
+    ``cap_d0 = batch_size * (1 + fanouts[-1])`` destination rows for the input layer and ``cap_d0 * fanouts[0]`` /
+    ``batch_size * fanouts[-1]`` edges.  Loading a mini-batch copies its arrays into those buffers on the device (no
+    read-back): rows past the real count get degree 0 (they aggregate to zero and receive zero gradient), unused edge
+    slots of the output-layer block hold the padding column id that ``dgllb_csr_transpose`` drops, padded seeds of a
+    short last batch are masked out of the loss.  The result is the same update as the eager step (checked in
+    tests/test_gpu_layers.py) with the host doing ~10 small copies and one graph launch per mini-batch instead of
+    ~100 Python-dispatched calls — the eager epoch is host-bound.
+
+    2-layer ``dgll_b200.nn.GraphSAGE`` with the gather-fused input layer (``feat_table``); the optimizer is captured
+    too when it is capturable (``torch.optim.Adam(..., fused=True, capturable=True)``) and there is no gradient
+    all-reduce, otherwise it (and the all-reduce) run eagerly after the replay."""
+
+    def __init__(self, model, opt, table, labels, batch_size=1024, fanouts=(25, 10), group=None, precision=None):
+        if len(fanouts) != 2 or len(model.layers) != 2:
+            raise ValueError("GraphedSageTrainer: 2-layer models / two fanouts")
+        dev = table.device
+        self.model, self.opt, self.table, self.labels, self.group = model, opt, table, labels, group
+        self.B = int(batch_size)
+        self.cap_d0 = self.B * (1 + int(fanouts[-1]))
+        self.cap_e0 = self.cap_d0 * int(fanouts[0])
+        self.cap_e1 = self.B * int(fanouts[-1])
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        i64, i32 = torch.int64, torch.int32
+        self.seeds = torch.zeros(self.B, dtype=i64, device=dev)
+        self.valid = torch.ones(self.B, dtype=torch.bool, device=dev)
+        self.rp0 = torch.zeros(self.cap_d0 + 1, dtype=i32, device=dev)
+        self.col0 = torch.zeros(self.cap_e0, dtype=i32, device=dev)
+        self.ids0 = torch.zeros(self.cap_d0, dtype=i64, device=dev)
+        self.rp1 = torch.zeros(self.B + 1, dtype=i32, device=dev)
+        self.col1 = torch.full((self.cap_e1,), self.cap_d0, dtype=i32, device=dev)
+        self.loss = torch.zeros((), device=dev)
+        self.loss_sum = torch.zeros((), device=dev)
+        self.graph = None
+        self._precision = precision
+        world = parallel.dist.get_world_size(group) if parallel.dist.is_initialized() else 1
+        self._opt_in_graph = world == 1 and bool(opt.defaults.get("capturable", False))
+
+    def _blocks(self):
+        b0 = G.Block(self.rp0, self.col0, self.col0, self.ids0, self.cap_d0)
+        b1 = G.Block(self.rp1, self.col1, self.col1, self.ids0, self.B)
+        return [b0, b1]
+
+    def load(self, seeds, blocks):
+        """Copy one mini-batch into the capture buffers (device-side, stream-ordered, no synchronisation)."""
+        b0, b1 = blocks
+        n0, n1, ns = b0.num_dst, b1.num_dst, seeds.numel()
+        e0, e1 = b0.col_global.numel(), b1.col.numel()
+        if n0 > self.cap_d0 or e0 > self.cap_e0 or e1 > self.cap_e1 or ns > self.B or n1 != ns:
+            raise ValueError("GraphedSageTrainer: mini-batch exceeds the captured capacities")
+        self.seeds[:ns].copy_(seeds)
+        if ns < self.B:
+            self.seeds[ns:].zero_()
+        self.valid[:ns] = True
+        self.valid[ns:] = False
+        self.rp0[:n0 + 1].copy_(b0.row_ptr)
+        self.rp0[n0 + 1:].copy_(b0.row_ptr[-1:].expand(self.cap_d0 - n0))
+        self.col0[:e0].copy_(b0.col_global)
+        self.ids0[:n0].copy_(b0.src_ids[:n0])
+        self.ids0[n0:].zero_()
+        self.rp1[:n1 + 1].copy_(b1.row_ptr)
+        if n1 < self.B:
+            self.rp1[n1 + 1:].copy_(b1.row_ptr[-1:].expand(self.B - n1))
+        self.col1[:e1].copy_(b1.col)
+        self.col1[e1:].fill_(self.cap_d0)
+
+    def _step_body(self):
+        logits = self.model(self._blocks(), None, feat_table=self.table)
+        target = torch.where(self.valid, self.labels[self.seeds], torch.full_like(self.seeds, -100))
+        loss = torch.nn.functional.cross_entropy(logits, target, ignore_index=-100)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+        self.loss_sum += loss.detach()
+        if self._opt_in_graph:
+            self.opt.step()
+
+    def capture(self):
+        prev = None
+        if self._precision is not None:
+            prev = ops.get_gemm_precision()
+            ops.set_gemm_precision(self._precision)
+        self.model.train()
+        state = [p.detach().clone() for p in self.params]
+        # optimizer state must exist BEFORE the capture (state created inside it would be re-zeroed by every replay):
+        # the warm-up steps create it, then it is put back to its pre-warm-up values in place
+        saved = {p: {k: v.detach().clone() for k, v in self.opt.state[p].items() if torch.is_tensor(v)}
+                 for p in self.params if p in self.opt.state}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up off the capture stream (allocator, lazy init)
+            for _ in range(2):
+                self.opt.zero_grad(set_to_none=True)
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():                               # the warm-up must not count as training
+            for p, s in zip(self.params, state):
+                p.copy_(s)
+        if self._opt_in_graph:
+            for p in self.params:
+                for k, v in self.opt.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        if p in saved and k in saved[p]:
+                            v.copy_(saved[p][k])
+                        else:
+                            v.zero_()
+        self.loss_sum.zero_()
+        self.opt.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+        if prev is not None:
+            ops.set_gemm_precision(prev)
+
+    def step(self):
+        """Replay the captured step on the loaded mini-batch."""
+        self.graph.replay()
+        if not self._opt_in_graph:
+            parallel.allreduce_gradients(self.params, group=self.group)
+            self.opt.step()
+
+    def epoch(self, batches):
+        """One epoch over pre-sampled ``batches`` (``make_batches``) or any iterable of (seeds, blocks)."""
+        if self.graph is None:
+            first = batches[0] if isinstance(batches, (list, tuple)) else None
+            if first is not None:
+                self.load(*first)
+            self.capture()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter()
+        self.loss_sum.zero_()
+        e0.record()
+        n = 0
+        for s, blocks in batches:
+            self.load(s, blocks)
+            self.step()
+            n += 1
+        e1.record()
+        torch.cuda.synchronize()
+        return {"time_s": e0.elapsed_time(e1) * 1e-3, "wall_s": time.perf_counter() - t_wall, "n_batches": n,
+                "loss": float(self.loss_sum.item()) / max(n, 1)}

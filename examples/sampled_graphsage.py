@@ -23,7 +23,7 @@ def main(n=50000, deg=30, feats=100, classes=10, batches=30, seed=0):
     loader = BlockDataLoader(graph, torch.arange(n // 2, device=dev), NeighborSampler([25, 10]), batch_size=1024,
                              shuffle=True, drop_last=True)
     model = GraphSAGE(feats, 128, classes, 2, torch.relu, 0.0).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=0.003)
+    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
     ops.set_gemm_precision("bf16")                                     # tcgen05 tensor cores for the dense transforms
     losses = []
     for step, (input_nodes, output_nodes, mfgs) in enumerate(loader):

@@ -146,6 +146,9 @@ int dgllb_spmm_max_backward(const int32_t* col_idx, const int32_t* argmax,
  * t_col_idx int32[nnz], t_values float[nnz] or NULL (ones when values == NULL),
  * perm int32[nnz] or NULL.  Within a transposed row, edges keep source-row
  * order (stable), so the result is deterministic.  nnz must be < 2^31-1.
+ * Entries whose column id equals n_cols are padding: they belong to no row of the
+ * result (t_row_ptr[n_cols] = number of real entries), so a fixed-capacity edge
+ * array padded with n_cols can be transposed without knowing its fill on the host.
  * Workspace comes from the stream-ordered allocator (cudaMallocAsync).
  */
 int dgllb_csr_transpose(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,

@@ -681,6 +681,33 @@ def test_gemm_tcgen05_bf16_parity(K, M, N, K_):
     assert rel_err(o2, gr @ br.T) <= 2e-5
 
 
+@pytest.mark.parametrize("M,N,K_", [(256, 602, 11264), (41, 256, 11264), (130, 70, 5000), (128, 128, 512)])
+def test_gemm_tcgen05_split_k(K, M, N, K_):
+    """Few output tiles + a long reduction (dW = X^T G of a training step): the k-blocks are split over CTAs, partials
+    summed in a fixed order by a second kernel.  Same bar as the unsplit kernel, epilogue / accumulate honoured,
+    run-to-run bit-identical (no atomics)."""
+    rng = np.random.default_rng(M + K_)
+    x = rng.standard_normal((K_, M)).astype(np.float32)          # stored [K, M]: trans_a
+    g = rng.standard_normal((K_, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    xr = dev(x).to(torch.bfloat16).float().cpu().numpy().astype(np.float64)
+    gr = dev(g).to(torch.bfloat16).float().cpu().numpy().astype(np.float64)
+    ref = xr.T @ gr
+    out = K.gemm(dev(x), dev(g), trans_a=True, precision="bf16")
+    assert rel_err(out.cpu().numpy(), ref) <= 2e-5
+    assert rel_err(out.cpu().numpy(), x.astype(np.float64).T @ g.astype(np.float64)) <= BF16_TOL
+    again = K.gemm(dev(x), dev(g), trans_a=True, precision="bf16")
+    assert torch.equal(out, again)
+    acc = rng.standard_normal((M, N)).astype(np.float32)
+    o = dev(acc)
+    K.gemm(dev(x), dev(g), trans_a=True, out=o, accumulate=True, bias=dev(bias), relu=True, precision="bf16")
+    assert rel_err(o.cpu().numpy(), np.maximum(acc + ref + bias, 0)) <= 2e-5
+    # output with a leading dimension (column slice of a wider buffer)
+    wide = torch.zeros((M, N + 9), device="cuda")
+    K.gemm(dev(x), dev(g), trans_a=True, out=wide[:, :N], precision="bf16")
+    assert rel_err(wide[:, :N].cpu().numpy(), ref) <= 2e-5 and (wide[:, N:] == 0).all()
+
+
 def test_layers_run_on_tensor_core_path(K):
     """ops.set_gemm_precision('bf16') routes every dense transform of a layer through tcgen05; GCN output stays within
     the bf16 bar of the fp32 path."""

@@ -535,3 +535,47 @@ def test_pipelined_epoch_equals_sequential_epoch(nn):
     assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"])
     for p, q in zip(m1.parameters(), m2.parameters()):
         assert torch.equal(p, q)
+
+
+# ------------------------------------------------- CUDA-graph training step --
+@pytest.mark.parametrize("optimizer", ["sgd_eager_step", "adam_captured"])
+def test_graphed_training_step_equals_eager_epoch(nn, optimizer):
+    """train.GraphedSageTrainer replays ONE captured step on fixed-capacity block buffers (rows past the real count
+    have degree 0, unused edge slots hold the padding column the transpose drops, a short last batch is masked out of
+    the loss).  Same losses and weights as the eager loop on the same pre-sampled mini-batches (fp32 GEMMs)."""
+    import copy
+    from dgll_b200 import graphs as G, train as T
+    N, F = 20000, 100
+    rp, col = G.rmat_csr(N, N * 20, seed=1, device="cuda")
+    table = G.feature_table(N, F, seed=2)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    labels = torch.randint(0, 7, (N,), device="cuda", generator=gen)
+    seeds = torch.randperm(N, device="cuda", generator=gen)[:512 * 5 + 77]        # short last batch
+    torch.manual_seed(0)
+    m1 = nn.GraphSAGE(F, 64, 7, 2, torch.relu, 0.0).cuda()
+    m2 = copy.deepcopy(m1)
+    if optimizer == "adam_captured":
+        o1 = torch.optim.Adam(m1.parameters(), lr=0.01, fused=True)
+        o2 = torch.optim.Adam(m2.parameters(), lr=0.01, fused=True, capturable=True)
+    else:
+        o1 = torch.optim.SGD(m1.parameters(), lr=0.05)
+        o2 = torch.optim.SGD(m2.parameters(), lr=0.05)
+    pre = T.make_batches(rp, col, seeds, (10, 5), 512, rng_seed=4)
+    assert len(pre) == 6 and pre[-1][0].numel() == 77
+    a = T.sage_epoch(m1, o1, table, labels, F, batches=pre, precision="fp32")
+    tr = T.GraphedSageTrainer(m2, o2, table, labels, 512, (10, 5), precision="fp32")
+    w0 = [p.detach().clone() for p in m2.parameters()]
+    tr.load(*pre[0])
+    tr.capture()
+    for p, q in zip(m2.parameters(), w0):
+        assert torch.equal(p, q)                     # capture (with its warm-up steps) leaves the weights untouched
+    b = tr.epoch(pre)
+    assert a["n_batches"] == b["n_batches"] == 6
+    assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"])
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        assert rel_err(q.detach().cpu().numpy(), p.detach().cpu().numpy()) <= 2e-5
+    # a second epoch through the sampler-in-the-loop iterator replays the same graph
+    c = tr.epoch(T.iter_batches(rp, col, seeds, (10, 5), 512, rng_seed=9))
+    assert c["n_batches"] == 6 and np.isfinite(c["loss"])
+    with pytest.raises(ValueError):
+        tr.load(seeds[:600], pre[0][1])              # more seeds than the captured capacity

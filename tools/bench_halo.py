@@ -80,7 +80,7 @@ def main():
     hx = P.PeerShardedTable(N, table) if args.halo == "peer" else P.HaloExchange(N, table)
     torch.manual_seed(0)
     model = dnn.GraphSAGE(F, hidden, C, 2, torch.relu, 0.0).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=0.003)
+    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
     params = list(model.parameters())
     ops.set_gemm_precision(args.precision)
 

@@ -15,7 +15,7 @@ seeds = torch.randperm(int(0.66 * N), device=dev, generator=gen)[:1024 * 40]
 model = dnn.GraphSAGE(F, 256, 41, 2, torch.relu, 0.0).to(dev)
 from dgll_b200 import ops
 ops.set_gemm_precision("bf16")
-opt = torch.optim.Adam(model.parameters(), lr=0.003)
+opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
 pre = T.make_batches(rp, col, seeds, (25, 10), 1024, rng_seed=3)
 T.sage_epoch(model, opt, table, labels, F, batches=pre[:8])
 pr = cProfile.Profile()
@@ -23,4 +23,5 @@ pr.enable()
 r = T.sage_epoch(model, opt, table, labels, F, batches=pre)
 pr.disable()
 print(r)
-pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(40)
