@@ -101,14 +101,20 @@ class GraphedSageTrainer:
     tests/test_gpu_layers.py) with the host doing ~10 small copies and one graph launch per mini-batch instead of
     ~100 Python-dispatched calls — the eager epoch is host-bound.
 
-    2-layer ``dgll_b200.nn.GraphSAGE`` with the gather-fused input layer (``feat_table``); the optimizer is captured
-    too when it is capturable (``torch.optim.Adam(..., fused=True, capturable=True)``) and there is no gradient
-    all-reduce, otherwise it (and the all-reduce) run eagerly after the replay."""
+    2-layer ``dgll_b200.nn.GraphSAGE``.  Input features either come straight from a resident ``table`` (gather fused
+    into the input layer's aggregation) or, with ``table=None, n_feat=F``, as the rows of the block's source nodes
+    handed to ``load(..., x=)`` — the partitioned case, where they were just fetched from the owning GPUs
+    (``parallel.PeerShardedTable``).  The optimizer is captured too when it is capturable
+    (``torch.optim.Adam(..., fused=True, capturable=True)``) and there is no gradient all-reduce, otherwise it (and
+    the all-reduce) run eagerly after the replay."""
 
-    def __init__(self, model, opt, table, labels, batch_size=1024, fanouts=(25, 10), group=None, precision=None):
+    def __init__(self, model, opt, table, labels, batch_size=1024, fanouts=(25, 10), group=None, precision=None,
+                 n_feat=None):
         if len(fanouts) != 2 or len(model.layers) != 2:
             raise ValueError("GraphedSageTrainer: 2-layer models / two fanouts")
-        dev = table.device
+        if table is None and n_feat is None:
+            raise ValueError("GraphedSageTrainer: pass the resident feature table, or n_feat for per-batch feature rows")
+        dev = labels.device if table is None else table.device
         self.model, self.opt, self.table, self.labels, self.group = model, opt, table, labels, group
         self.B = int(batch_size)
         self.cap_d0 = self.B * (1 + int(fanouts[-1]))
@@ -121,6 +127,11 @@ class GraphedSageTrainer:
         self.rp0 = torch.zeros(self.cap_d0 + 1, dtype=i32, device=dev)
         self.col0 = torch.zeros(self.cap_e0, dtype=i32, device=dev)
         self.ids0 = torch.zeros(self.cap_d0, dtype=i64, device=dev)
+        self.x = None
+        if table is None:
+            self.cap_src = self.cap_d0 * (1 + int(fanouts[0]))
+            self.x = torch.zeros((self.cap_src, int(n_feat)), dtype=torch.float32, device=dev)
+            self._src_shape = torch.empty(self.cap_src, dtype=torch.int8, device=dev)   # only its length is used
         self.rp1 = torch.zeros(self.B + 1, dtype=i32, device=dev)
         self.col1 = torch.full((self.cap_e1,), self.cap_d0, dtype=i32, device=dev)
         self.loss = torch.zeros((), device=dev)
@@ -131,17 +142,23 @@ class GraphedSageTrainer:
         self._opt_in_graph = world == 1 and bool(opt.defaults.get("capturable", False))
 
     def _blocks(self):
-        b0 = G.Block(self.rp0, self.col0, self.col0, self.ids0, self.cap_d0)
+        b0 = G.Block(self.rp0, self.col0, self.col0, self.ids0 if self.x is None else self._src_shape, self.cap_d0)
         b1 = G.Block(self.rp1, self.col1, self.col1, self.ids0, self.B)
         return [b0, b1]
 
-    def load(self, seeds, blocks):
-        """Copy one mini-batch into the capture buffers (device-side, stream-ordered, no synchronisation)."""
+    def load(self, seeds, blocks, x=None):
+        """Copy one mini-batch into the capture buffers (device-side, stream-ordered, no synchronisation).
+        ``x``: feature rows of ``blocks[0]``'s source nodes (per-batch feature mode only)."""
         b0, b1 = blocks
         n0, n1, ns = b0.num_dst, b1.num_dst, seeds.numel()
-        e0, e1 = b0.col_global.numel(), b1.col.numel()
+        col0 = b0.col_global if self.x is None else b0.col
+        e0, e1 = col0.numel(), b1.col.numel()
         if n0 > self.cap_d0 or e0 > self.cap_e0 or e1 > self.cap_e1 or ns > self.B or n1 != ns:
             raise ValueError("GraphedSageTrainer: mini-batch exceeds the captured capacities")
+        if self.x is not None:
+            if x is None or x.size(0) > self.cap_src or x.size(1) != self.x.size(1):
+                raise ValueError("GraphedSageTrainer: per-batch feature rows missing or larger than the capacity")
+            self.x[:x.size(0)].copy_(x)
         self.seeds[:ns].copy_(seeds)
         if ns < self.B:
             self.seeds[ns:].zero_()
@@ -149,9 +166,10 @@ class GraphedSageTrainer:
         self.valid[ns:] = False
         self.rp0[:n0 + 1].copy_(b0.row_ptr)
         self.rp0[n0 + 1:].copy_(b0.row_ptr[-1:].expand(self.cap_d0 - n0))
-        self.col0[:e0].copy_(b0.col_global)
-        self.ids0[:n0].copy_(b0.src_ids[:n0])
-        self.ids0[n0:].zero_()
+        self.col0[:e0].copy_(col0)
+        if self.x is None:
+            self.ids0[:n0].copy_(b0.src_ids[:n0])
+            self.ids0[n0:].zero_()
         self.rp1[:n1 + 1].copy_(b1.row_ptr)
         if n1 < self.B:
             self.rp1[n1 + 1:].copy_(b1.row_ptr[-1:].expand(self.B - n1))
@@ -159,7 +177,10 @@ class GraphedSageTrainer:
         self.col1[e1:].fill_(self.cap_d0)
 
     def _step_body(self):
-        logits = self.model(self._blocks(), None, feat_table=self.table)
+        if self.x is None:
+            logits = self.model(self._blocks(), None, feat_table=self.table)
+        else:
+            logits = self.model(self._blocks(), self.x)
         target = torch.where(self.valid, self.labels[self.seeds], torch.full_like(self.seeds, -100))
         loss = torch.nn.functional.cross_entropy(logits, target, ignore_index=-100)
         loss.backward()
@@ -214,7 +235,7 @@ class GraphedSageTrainer:
             self.opt.step()
 
     def epoch(self, batches):
-        """One epoch over pre-sampled ``batches`` (``make_batches``) or any iterable of (seeds, blocks)."""
+        """One epoch over pre-sampled ``batches`` (``make_batches``) or any iterable of (seeds, blocks[, x])."""
         if self.graph is None:
             first = batches[0] if isinstance(batches, (list, tuple)) else None
             if first is not None:
@@ -226,8 +247,8 @@ class GraphedSageTrainer:
         self.loss_sum.zero_()
         e0.record()
         n = 0
-        for s, blocks in batches:
-            self.load(s, blocks)
+        for item in batches:
+            self.load(*item)
             self.step()
             n += 1
         e1.record()

@@ -25,7 +25,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import dgll_b200.nn as dnn  # noqa: E402
-from dgll_b200 import graphs as G, ops, parallel as P  # noqa: E402
+from dgll_b200 import graphs as G, ops, parallel as P, train as T  # noqa: E402
 
 
 def main():
@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--graph", default="uniform", choices=["uniform", "rmat"])
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph = the training step replayed as one CUDA graph on fixed-capacity buffers "
+                         "(train.GraphedSageTrainer); eager = Python-dispatched step")
     ap.add_argument("--halo", default="peer", choices=["padded", "exact", "peer"],
                     help="peer = shards mapped over NVLink (CUDA IPC), ONE gather kernel pulls remote rows; exact = NCCL "
                          "all_to_all with counts exchanged first; padded = NCCL with fixed-capacity buckets, no host sync")
@@ -80,23 +83,38 @@ def main():
     hx = P.PeerShardedTable(N, table) if args.halo == "peer" else P.HaloExchange(N, table)
     torch.manual_seed(0)
     model = dnn.GraphSAGE(F, hidden, C, 2, torch.relu, 0.0).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=(world == 1 and args.mode == "graph"))
     params = list(model.parameters())
     ops.set_gemm_precision(args.precision)
+    fetch = (lambda ids: hx.fetch_padded(ids)) if args.halo == "padded" else (lambda ids: hx.fetch(ids))
+    trainer, mode, mode_err = None, args.mode, None
+    if args.mode == "graph":
+        try:
+            trainer = T.GraphedSageTrainer(model, opt, None, labels, args.batch, fanouts, n_feat=F)
+            b0 = G.sample_blocks(row_ptr, col, seeds_all[:args.batch], fanouts, rng_seed=999 + rank)
+            trainer.load(seeds_all[:args.batch], b0, fetch(b0[0].src_ids))
+            trainer.capture()
+        except Exception as ex:   # keep the run: fall back to the eager step and say so in the JSON line
+            trainer, mode, mode_err = None, "eager", "%s: %s" % (type(ex).__name__, str(ex)[:160])
+            opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
 
     def one_step(i, ev=None):
         s = seeds_all[i * args.batch:(i + 1) * args.batch]
         if ev: ev[0].record()
         blocks = G.sample_blocks(row_ptr, col, s, fanouts, rng_seed=rank * 100003 + i)
         if ev: ev[1].record()
-        x = hx.fetch_padded(blocks[0].src_ids) if args.halo == "padded" else hx.fetch(blocks[0].src_ids)  # peer: ONE kernel
+        x = fetch(blocks[0].src_ids)                                           # peer: ONE kernel
         if ev: ev[2].record()
-        logits = model(blocks, x)
-        loss = torch.nn.functional.cross_entropy(logits, labels[s])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        P.allreduce_gradients(params)
-        opt.step()
+        if trainer is not None:
+            trainer.load(s, blocks, x)
+            trainer.step()                      # graph replay (+ flat gradient all-reduce and Adam when world > 1)
+        else:
+            logits = model(blocks, x)
+            loss = torch.nn.functional.cross_entropy(logits, labels[s])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            P.allreduce_gradients(params)
+            opt.step()
         if ev: ev[3].record()
         return blocks[0].num_src, blocks[0].num_edges()
 
@@ -148,7 +166,7 @@ def main():
             "remote_row_fraction": remote,
             "halo_bytes_in_per_gpu_per_step": rows_per_step * remote * F * 4,
             "config": {"N": N, "nnz": NNZ, "F": F, "fanouts": list(fanouts), "batch_per_gpu": args.batch, "hidden": hidden,
-                       "graph": args.graph, "gemm": args.precision, "halo": args.halo, "halo_overflow": hx_overflow(), "peer_vs_nccl_bit_exact": verified, "scale": args.scale, "setup_s": round(setup_s, 1)},
+                       "graph": args.graph, "gemm": args.precision, "step": mode, "step_fallback_reason": mode_err, "halo": args.halo, "halo_overflow": hx_overflow(), "peer_vs_nccl_bit_exact": verified, "scale": args.scale, "setup_s": round(setup_s, 1)},
             "scaling": "weak"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
