@@ -37,42 +37,60 @@ struct PackOperand {
     unsigned blocks_x;   // ceil(rows / 32)
 };
 
+// One block packs a 32 (rows) x 64 (k) tile of one operand.
+//   direct     : thread = (row, 8 consecutive k): two 16-byte loads -> one 16-byte store of 8 bf16 (vector path when the
+//                source rows are 16-byte aligned), 256 B read / 128 B written per row per tile
+//   transposed : the tile goes through shared memory: reads coalesced along rows (128 B), writes 128 B along k
 __device__ __forceinline__ void pack_tile(const PackOperand& o, unsigned bx, unsigned by, int K, int Kp,
                                           float (*tile)[33]) {
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const long long r0 = static_cast<long long>(bx) * 32;
-    const int k0 = by * 32;
+    const int k0 = by * 64;
     if (o.transposed) {
-        // read src[k0+j, r0+tx] coalesced along r, write dst[r0+j', k0+tx] coalesced along k
-        for (int j = ty; j < 32; j += 8) {
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+        for (int j = ty; j < 64; j += 8) {
             const int k = k0 + j;
             const long long r = r0 + tx;
             tile[j][tx] = (k < K && r < o.rows) ? __ldg(o.src + static_cast<long long>(k) * o.ld + r) : 0.f;
         }
         __syncthreads();
-        for (int j = ty; j < 32; j += 8) {
-            const long long r = r0 + j;
-            const int k = k0 + tx;
-            if (r < o.rows && k < Kp) o.dst[r * Kp + k] = __float2bfloat16(tile[tx][j]);
+        // 32 rows x 64 k: thread (row = tid / 8, k-octet = tid % 8) writes 8 bf16 = 16 bytes
+        const int row = threadIdx.x >> 3, oct = threadIdx.x & 7;
+        const long long r = r0 + row;
+        const int k = k0 + oct * 8;
+        if (r < o.rows && k < Kp) {   // Kp is a multiple of 64: the whole octet is inside the padded row
+            __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) v[a] = __float2bfloat16(tile[oct * 8 + a][row]);
+            *reinterpret_cast<uint4*>(o.dst + r * Kp + k) = *reinterpret_cast<const uint4*>(v);
         }
     } else {
-        for (int j = ty; j < 32; j += 8) {
-            const long long r = r0 + j;
-            const int k = k0 + tx;
-            if (r < o.rows && k < Kp) {
-                const float v = k < K ? __ldg(o.src + r * o.ld + k) : 0.f;
-                o.dst[r * Kp + k] = __float2bfloat16(v);
-            }
+        const int row = threadIdx.x >> 3, oct = threadIdx.x & 7;
+        const long long r = r0 + row;
+        const int k = k0 + oct * 8;
+        if (r >= o.rows || k >= Kp) return;
+        const float* src = o.src + r * o.ld + k;
+        float f[8];
+        if (k + 8 <= K && (o.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(o.src) & 15) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) f[a] = (k + a < K) ? __ldg(src + a) : 0.f;
         }
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) v[a] = __float2bfloat16(f[a]);
+        *reinterpret_cast<uint4*>(o.dst + r * Kp + k) = *reinterpret_cast<const uint4*>(v);
     }
 }
 
 // BOTH operands in one launch: blocks [0, a.blocks_x) of the x dimension pack A, the rest pack B (the small GEMMs of a
 // training step are launch-latency bound: 4.5 us per pack launch against ~1 us of work).
-// dst[r, k] (bf16, row stride Kp) = transposed ? src[k, r] : src[r, k];  zero for k >= K.  32x32 tiles through smem.
+// dst[r, k] (bf16, row stride Kp) = transposed ? src[k, r] : src[r, k];  zero for k >= K.
 __global__ void __launch_bounds__(256)
 pack_bf16_kernel(const PackOperand a, const PackOperand b, int K, int Kp) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][33];
     if (blockIdx.x < a.blocks_x) pack_tile(a, blockIdx.x, blockIdx.y, K, Kp, tile);
     else pack_tile(b, blockIdx.x - a.blocks_x, blockIdx.y, K, Kp, tile);
 }
@@ -348,7 +366,7 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
         // B operand: rows = N, K-major (= B^T).  stored [K,N] -> transpose; stored [N,K] (transB) -> direct
         pb.src = B; pb.ld = ldb; pb.rows = N; pb.dst = Bb; pb.transposed = transB ? 0 : 1;
         pb.blocks_x = static_cast<unsigned>((N + 31) / 32);
-        const dim3 gp(pa.blocks_x + pb.blocks_x, static_cast<unsigned>((Kp + 31) / 32));
+        const dim3 gp(pa.blocks_x + pb.blocks_x, static_cast<unsigned>(Kp / 64));
         if (gp.y > 65535u) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: K too large"); break; }
         pack_bf16_kernel<<<gp, 256, 0, st>>>(pa, pb, static_cast<int>(K), Kp);
         g_launch_count.fetch_add(1);

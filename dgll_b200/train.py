@@ -234,24 +234,84 @@ class GraphedSageTrainer:
             parallel.allreduce_gradients(self.params, group=self.group)
             self.opt.step()
 
-    def epoch(self, batches):
-        """One epoch over pre-sampled ``batches`` (``make_batches``) or any iterable of (seeds, blocks[, x])."""
+    def epoch(self, batches, overlap=None, callback=None):
+        """One epoch over pre-sampled ``batches`` (``make_batches``) or any iterable of (seeds, blocks[, x]).
+
+        ``overlap`` (default: on for iterators, off for lists): mini-batch i+1 is PRODUCED — whatever the iterator does:
+        device sampler, block builder, feature fetch from the peers — on a side stream while the GPU replays step i.
+        The producer's read-backs then synchronise only the side stream, so the host no longer waits for the training
+        graph before it can sample the next batch; the copy into the capture buffers stays on the main stream, ordered
+        after the previous replay.  ``callback(stage, i)`` with stage "before" (the load of step i is about to be
+        enqueued) / "after" (step i is enqueued) runs on the main stream — a hook for per-stage CUDA events."""
         if self.graph is None:
             first = batches[0] if isinstance(batches, (list, tuple)) else None
             if first is not None:
                 self.load(*first)
             self.capture()
+        if overlap is None:
+            overlap = not isinstance(batches, (list, tuple))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t_wall = time.perf_counter()
         self.loss_sum.zero_()
         e0.record()
         n = 0
-        for item in batches:
-            self.load(*item)
-            self.step()
-            n += 1
+        if not overlap:
+            for item in batches:
+                if callback:
+                    callback("before", n)
+                self.load(*item)
+                self.step()
+                if callback:
+                    callback("after", n)
+                n += 1
+        else:
+            main = torch.cuda.current_stream()
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            side.wait_stream(main)
+            it = iter(batches)
+
+            def produce():
+                with torch.cuda.stream(side):
+                    try:
+                        item = next(it)
+                    except StopIteration:
+                        return None
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                return item, ev
+
+            nxt = produce()
+            while nxt is not None:
+                item, ev = nxt
+                main.wait_event(ev)
+                if callback:
+                    callback("before", n)
+                self.load(*item)
+                for t in _tensors_of(item):
+                    t.record_stream(main)      # allocated on the side stream, read by the copies on the main stream
+                self.step()
+                if callback:
+                    callback("after", n)
+                n += 1
+                nxt = produce()                 # the host samples batch i+1 while the GPU replays step i
         e1.record()
         torch.cuda.synchronize()
         return {"time_s": e0.elapsed_time(e1) * 1e-3, "wall_s": time.perf_counter() - t_wall, "n_batches": n,
                 "loss": float(self.loss_sum.item()) / max(n, 1)}
+
+
+def _tensors_of(item):
+    """Every tensor of a (seeds, blocks[, x]) mini-batch."""
+    seeds, blocks = item[0], item[1]
+    out = [seeds]
+    for b in blocks:
+        for name in ("row_ptr", "col", "col_global", "src_ids"):
+            t = getattr(b, name, None)
+            if torch.is_tensor(t) and t.is_cuda:
+                out.append(t)
+    if len(item) > 2 and torch.is_tensor(item[2]):
+        out.append(item[2])
+    return out

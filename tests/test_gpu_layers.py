@@ -574,6 +574,20 @@ def test_graphed_training_step_equals_eager_epoch(nn, optimizer):
     assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"])
     for p, q in zip(m1.parameters(), m2.parameters()):
         assert rel_err(q.detach().cpu().numpy(), p.detach().cpu().numpy()) <= 2e-5
+    # production of batch i+1 on a side stream under the replay of step i (the default for iterators): same update,
+    # bit for bit, as the serial replay
+    m3 = copy.deepcopy(m1)
+    for p, q in zip(m3.parameters(), w0):
+        p.data.copy_(q)
+    o3 = (torch.optim.Adam(m3.parameters(), lr=0.01, fused=True, capturable=True) if optimizer == "adam_captured"
+          else torch.optim.SGD(m3.parameters(), lr=0.05))
+    tr3 = T.GraphedSageTrainer(m3, o3, table, labels, 512, (10, 5), precision="fp32")
+    tr3.load(*pre[0])
+    tr3.capture()
+    d = tr3.epoch(iter(pre))
+    assert d["n_batches"] == 6 and d["loss"] == b["loss"]
+    for p, q in zip(m2.parameters(), m3.parameters()):
+        assert torch.equal(p, q)
     # a second epoch through the sampler-in-the-loop iterator replays the same graph
     c = tr.epoch(T.iter_batches(rp, col, seeds, (10, 5), 512, rng_seed=9))
     assert c["n_batches"] == 6 and np.isfinite(c["loss"])

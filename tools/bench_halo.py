@@ -39,6 +39,9 @@ def main():
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph = the training step replayed as one CUDA graph on fixed-capacity buffers "
                          "(train.GraphedSageTrainer); eager = Python-dispatched step")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
+                    help="graph mode: produce step i+1 (sample, build blocks, fetch rows) on the main stream instead of a "
+                         "side stream that runs under the replay of step i")
     ap.add_argument("--halo", default="peer", choices=["padded", "exact", "peer"],
                     help="peer = shards mapped over NVLink (CUDA IPC), ONE gather kernel pulls remote rows; exact = NCCL "
                          "all_to_all with counts exchanged first; padded = NCCL with fixed-capacity buckets, no host sync")
@@ -118,8 +121,27 @@ def main():
         if ev: ev[3].record()
         return blocks[0].num_src, blocks[0].num_edges()
 
-    for w in range(args.warmup):
-        one_step(w)
+    def produce(first, count, evs=None):
+        """(seeds, blocks, x) per step — sampling, block building and the halo fetch; runs on the trainer's side stream
+        when the production of step i+1 overlaps the replay of step i (events are recorded on whatever stream is current)."""
+        for k in range(count):
+            i = first + k
+            s = seeds_all[i * args.batch:(i + 1) * args.batch]
+            if evs: evs[k][0].record()
+            blocks = G.sample_blocks(row_ptr, col, s, fanouts, rng_seed=rank * 100003 + i)
+            if evs: evs[k][1].record()
+            x = fetch(blocks[0].src_ids)
+            if evs: evs[k][2].record()
+            counts[0] += blocks[0].num_src
+            counts[1] += blocks[0].num_edges()
+            yield s, blocks, x
+
+    counts = [0, 0]
+    if trainer is not None:
+        trainer.epoch(produce(0, args.warmup), overlap=args.overlap)
+    else:
+        for w in range(args.warmup):
+            one_step(w)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -134,21 +156,34 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         verified = bool(ok.item())
         assert verified, "peer gather and NCCL halo exchange disagree"
+        hx.stats = {"rows": 0, "remote_rows": 0, "calls": 0}
     hx_overflow = (lambda: hx.check_overflow()) if hasattr(hx, "check_overflow") else (lambda: False)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    n_src = n_edge = 0
-    for i in range(args.steps):
-        a, b = one_step(args.warmup + i, evs[i])
-        n_src += a
-        n_edge += b
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    stage = [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / args.steps for k in range(3)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    counts = [0, 0]
+    if trainer is not None:
+        def cb(stage, i):
+            evs[i][3 if stage == "before" else 4].record()
+        r = trainer.epoch(produce(args.warmup, args.steps, evs), overlap=args.overlap, callback=cb)
+        ms = r["time_s"] * 1e3
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        stage = [sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps, sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps,
+                 sum(e[3].elapsed_time(e[4]) for e in evs) / args.steps]
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            a, b = one_step(args.warmup + i, evs[i])
+            counts[0] += a
+            counts[1] += b
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        stage = [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / args.steps for k in range(3)]
+    n_src, n_edge = counts
     t = torch.tensor([ms] + stage, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -166,7 +201,8 @@ def main():
             "remote_row_fraction": remote,
             "halo_bytes_in_per_gpu_per_step": rows_per_step * remote * F * 4,
             "config": {"N": N, "nnz": NNZ, "F": F, "fanouts": list(fanouts), "batch_per_gpu": args.batch, "hidden": hidden,
-                       "graph": args.graph, "gemm": args.precision, "step": mode, "step_fallback_reason": mode_err, "halo": args.halo, "halo_overflow": hx_overflow(), "peer_vs_nccl_bit_exact": verified, "scale": args.scale, "setup_s": round(setup_s, 1)},
+                       "graph": args.graph, "gemm": args.precision, "step": mode, "step_fallback_reason": mode_err,
+                       "overlap_production_with_replay": bool(args.overlap and trainer is not None), "halo": args.halo, "halo_overflow": hx_overflow(), "peer_vs_nccl_bit_exact": verified, "scale": args.scale, "setup_s": round(setup_s, 1)},
             "scaling": "weak"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
