@@ -815,12 +815,13 @@ static int launch_gat_bwd(GatBwdParams& p, const dgllb_csr_plan* plan, const dgl
 
 template <int VE>
 static int launch_gat_fwd(GatParams& p, const dgllb_csr_plan* plan, cudaStream_t st) {
-    // whole-row kernel: all heads of a row in one warp (vector path, <= 4 heads, 64 < heads*D <= 512).  On a uniform
+    // whole-row kernel: all heads of a row in one warp (vector path, <= 4 heads, 32 <= heads*D <= 512; the only forward
+    // kernel that takes the long-row plan, which is what a 47-class output layer on a skewed graph needs).  On a uniform
     // degree-50 graph it runs at the SpMM rate (20.5 ms vs 19.2 ms, products-sized); on skewed graphs it needs the
     // nnz-split plan for long rows (a 89K-edge row would otherwise be one warp's job).  DGLLB_GAT_KERNEL=group|row pins.
     const int FD = p.heads * p.D;
     const char* force = getenv("DGLLB_GAT_KERNEL");
-    const bool row_ok = VE == 4 && p.heads <= 4 && FD > 64 && FD <= 512;
+    const bool row_ok = VE == 4 && p.heads <= 4 && FD >= 32 && FD <= 512;  // below 32 floats most lanes of a warp would idle
     if (row_ok && !(force && force[0] == 'g')) {
         const bool heavy = plan && plan->n_heavy_rows > 0;
         float* ws = nullptr;

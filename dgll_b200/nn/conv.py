@@ -167,6 +167,35 @@ def _attn_dropout(p, training):
     return float(p) if (training and p > 0) else 0.0
 
 
+def _fused_attention(x, adj, Ws, a_ls, a_rs, slope, mode, elu, dropout):
+    """All heads of one attention layer: ``[Wh | el | er] = x @ [W_1..W_H | W_h a_l,h | W_h a_r,h]`` in ONE dense
+    transform (``el_h = (x W_h) a_l,h = x (W_h a_l,h)``: the score projections are folded into the weight matrix, a
+    parameter-sized product), then the fused aggregation on that buffer (``ops.gat_aggregate_ext``).  Head widths that
+    are not a multiple of 4 are zero-padded to one so the kernels take their 128-bit path; the pad columns are
+    dropped from the result.  Falls back to separate tensors on non-square graphs (blocks)."""
+    H, D = len(Ws), Ws[0].size(1)
+    graph = ops.as_csr(adj, binary=True)
+    if graph.n_dst != graph.n_src:
+        Wh = ops.linear(x, torch.cat(list(Ws), dim=1) if H > 1 else Ws[0])
+        Whv = Wh.view(-1, H, D)
+        el = (Whv * torch.stack(list(a_ls))).sum(-1)
+        er = (Whv * torch.stack(list(a_rs))).sum(-1)
+        return ops.gat_aggregate(graph, Wh, el.contiguous(), er.contiguous(), heads=H, slope=slope, mode=mode, elu=elu,
+                                 dropout=dropout)
+    Dp = (D + 3) // 4 * 4
+    cols = [W if Dp == D else Fn.pad(W, (0, Dp - D)) for W in Ws]
+    cols += [(W @ a)[:, None] for W, a in zip(Ws, a_ls)]
+    cols += [(W @ a)[:, None] for W, a in zip(Ws, a_rs)]
+    width = H * Dp + 2 * H
+    if width % 4:
+        cols.append(x.new_zeros((Ws[0].size(0), 4 - width % 4)))
+    ext = ops.linear(x, torch.cat(cols, dim=1))
+    out = ops.gat_aggregate_ext(graph, ext, H, Dp, slope=slope, mode=mode, elu=elu, dropout=dropout)
+    if Dp != D:
+        out = out.view(-1, H, Dp)[:, :, :D].reshape(-1, H * D)
+    return out
+
+
 class gatConv(F.nn.Module):
     """gatconv.py:10-57 — dense-adjacency GAT layer; attention = softmax over ``adj > 0`` of
     ``leakyrelu(Wh a[:D] + (Wh a[D:])^T)``.  The N x N score matrix is never formed: the kernel walks the edges."""
@@ -181,17 +210,10 @@ class gatConv(F.nn.Module):
         F.init.xavier_uniform_(self.a.data, gain=1.414)
         self.leakyrelu = F.LeakyReLU(self.alpha)
 
-    def _scores(self, Wh):
-        D = self.out_features
-        a = self.a.reshape(2 * D, 1)
-        e = ops.linear(Wh, torch.cat([a[:D], a[D:]], dim=1))      # [N, 2]: (Wh.a1, Wh.a2) in one GEMM
-        return e[:, 0:1].contiguous(), e[:, 1:2].contiguous()
-
     def forward(self, h, adj):
-        Wh = ops.linear(h, self.W)
-        el, er = self._scores(Wh)
-        return ops.gat_aggregate(adj, Wh, el, er, heads=1, slope=self.alpha, mode="softmax", elu=self.concat,
-                                 dropout=_attn_dropout(self.dropout, self.training))
+        D = self.out_features
+        return _fused_attention(h, adj, [self.W], [self.a[:D, 0]], [self.a[D:, 0]], self.alpha, "softmax", self.concat,
+                                _attn_dropout(self.dropout, self.training))
 
     def __repr__(self):
         return "%s (%d -> %d)" % (self.__class__.__name__, self.in_features, self.out_features)
@@ -255,12 +277,8 @@ class sparseGatConv(F.nn.Module):
 
     def forward(self, input, adj):
         D = self.out_features
-        h = ops.linear(input, self.W)
-        a2 = self.a.reshape(2, D).t()                               # [D, 2]: columns a[:D], a[D:]
-        e = ops.linear(h, a2)
-        el, er = e[:, 0:1].contiguous(), e[:, 1:2].contiguous()
-        return ops.gat_aggregate(adj, h, el, er, heads=1, slope=self.alpha, mode="exp_neg", elu=self.concat,
-                                 dropout=_attn_dropout(self.dropout.p, self.training))
+        return _fused_attention(input, adj, [self.W], [self.a[0, :D]], [self.a[0, D:]], self.alpha, "exp_neg",
+                                self.concat, _attn_dropout(self.dropout.p, self.training))
 
     def __repr__(self):
         return "%s (%d -> %d)" % (self.__class__.__name__, self.in_features, self.out_features)
@@ -273,21 +291,13 @@ class _MultiHeadMixin:
     def _heads_forward(self, x, adj, mode):
         atts = self.attentions
         D = atts[0].out_features
-        H = len(atts)
-        Wcat = torch.cat([m.W for m in atts], dim=1)                          # [in, H*D]
-        Wh = ops.linear(x, Wcat)
         if mode == "softmax":
-            a_l = torch.stack([m.a[:D, 0] for m in atts])                     # [H, D]
-            a_r = torch.stack([m.a[D:, 0] for m in atts])
+            a_l, a_r = [m.a[:D, 0] for m in atts], [m.a[D:, 0] for m in atts]
         else:
-            a_l = torch.stack([m.a[0, :D] for m in atts])
-            a_r = torch.stack([m.a[0, D:] for m in atts])
-        Whv = Wh.view(-1, H, D)
-        el = (Whv * a_l).sum(-1)
-        er = (Whv * a_r).sum(-1)
+            a_l, a_r = [m.a[0, :D] for m in atts], [m.a[0, D:] for m in atts]
         pdrop = atts[0].dropout.p if isinstance(atts[0].dropout, torch.nn.Dropout) else atts[0].dropout
-        return ops.gat_aggregate(adj, Wh, el.contiguous(), er.contiguous(), heads=H, slope=atts[0].alpha, mode=mode,
-                                 elu=True, dropout=_attn_dropout(pdrop, self.training))
+        return _fused_attention(x, adj, [m.W for m in atts], a_l, a_r, atts[0].alpha, mode, True,
+                                _attn_dropout(pdrop, self.training))
 
 
 class GAT(F.nn.Module, _MultiHeadMixin):

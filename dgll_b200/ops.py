@@ -319,6 +319,56 @@ class _GatFn(torch.autograd.Function):
         return d_wh, d_el, d_er, None, None, None, None, None, None
 
 
+class _GatExtFn(torch.autograd.Function):
+    """GAT aggregation on ONE activation buffer ``ext = [Wh | el | er | pad]`` ([n, heads*D + 2*heads (+pad)], produced by
+    a single dense transform): the kernels read the three parts in place through leading dimensions, and the backward
+    writes d_Wh, d_el, d_er into one buffer of the same layout, so the transform's backward is one pair of GEMMs and no
+    slice / cat / broadcast kernels run.  Square graphs only (el and er index the same node set)."""
+
+    @staticmethod
+    def forward(ctx, ext, graph, heads, D, slope, mode, dropout, seed):
+        FD = heads * D
+        wh, el, er = ext[:, :FD], ext[:, FD:FD + heads], ext[:, FD + heads:FD + 2 * heads]
+        out, rmax, rsum = K.gat_forward(graph.row_ptr, graph.col, wh, el, er, heads, slope, mode=mode,
+                                        save_stats=True, n_dst=graph.n_dst, plan=graph.bin_plan(), dropout=dropout,
+                                        seed=seed)
+        ctx.graph, ctx.heads, ctx.D, ctx.slope, ctx.mode = graph, heads, D, slope, mode
+        ctx.dropout, ctx.seed = dropout, seed
+        ctx.save_for_backward(ext, out, rmax, rsum)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        ext, out, rmax, rsum = ctx.saved_tensors
+        graph, heads, FD = ctx.graph, ctx.heads, ctx.heads * ctx.D
+        wh, el, er = ext[:, :FD], ext[:, FD:FD + heads], ext[:, FD + heads:FD + 2 * heads]
+        gt = graph.transpose()
+        d_ext = torch.empty_like(ext)
+        if ext.size(1) > FD + 2 * heads:
+            d_ext[:, FD + 2 * heads:].zero_()
+        K.gat_backward(graph.row_ptr, graph.col, gt.row_ptr, gt.col, graph._perm, wh, el, er, out, rmax, rsum,
+                       grad.contiguous(), heads, ctx.slope, mode=ctx.mode, d_ext=d_ext, dropout=ctx.dropout,
+                       seed=ctx.seed, plan=graph.gat_plan(), t_plan=gt.gat_plan())
+        return d_ext, None, None, None, None, None, None, None
+
+
+def gat_aggregate_ext(adj, ext, heads, D, slope=0.2, mode="softmax", elu=False, dropout=0.0, seed=None):
+    """``gat_aggregate`` for ``ext = [Wh | el | er | pad]`` rows (see ``_GatExtFn``); returns [n, heads*D]."""
+    graph = as_csr(adj, binary=True)
+    if graph.n_dst != graph.n_src or ext.size(0) != graph.n_src:
+        raise ValueError("gat_aggregate_ext: square graphs only")
+    if dropout and seed is None:
+        seed = _fresh_seed()
+    seed = seed or 0
+    FD = heads * D
+    if torch.is_grad_enabled() and ext.requires_grad:
+        out = _GatExtFn.apply(ext, graph, heads, D, slope, mode, float(dropout), seed)
+        return torch.nn.functional.elu(out) if elu else out
+    return K.gat_forward(graph.row_ptr, graph.col, ext[:, :FD], ext[:, FD:FD + heads], ext[:, FD + heads:FD + 2 * heads],
+                         heads, slope, mode=mode, elu=elu, n_dst=graph.n_dst, plan=graph.bin_plan(),
+                         dropout=float(dropout), seed=seed)
+
+
 def _fresh_seed():
     """64-bit seed from torch's CPU generator (follows torch.manual_seed; no device synchronisation)."""
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())

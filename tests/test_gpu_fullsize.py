@@ -178,6 +178,26 @@ def test_full_products_gat_properties(K):
     finally:
         os.environ.pop("DGLLB_GAT_KERNEL", None)
     assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1.0)
+    del b, ones
+    # zero attention vectors => every neighbour weighs 1/deg: the fused GAT layer IS the mean aggregation, forward and
+    # backward, so the two independent kernel families check each other at full size
+    zero = torch.zeros((Np, heads), device="cuda")
+    u, rmax, rsum = K.gat_forward(rp, col, wh, zero, zero, heads, 0.2, save_stats=True, plan=plan)
+    mean = K.spmm_csr(rp, col, wh, reduce="mean", plan=K.CsrPlan(rp, chunk_edges=4096))
+    scale = max(mean.abs().max().item(), 1.0)
+    assert (u - mean).abs().max().item() <= 2e-5 * scale
+    gout = torch.randn((Np, heads * D), device="cuda", generator=g)
+    trp, tcol, _, perm = K.csr_transpose(rp, col, Np, want_perm=True)
+    bp, btp = K.CsrPlan(rp, chunk_edges=256), K.CsrPlan(trp, chunk_edges=256)
+    d_wh, d_el, d_er = K.gat_backward(rp, col, trp, tcol, perm, wh, zero, zero, u, rmax, rsum, gout, heads, 0.2,
+                                      plan=bp, t_plan=btp)
+    inv = torch.where(deg > 0, 1.0 / deg.clamp(min=1).float(), torch.zeros_like(deg, dtype=torch.float32))
+    want = K.spmm_csr(trp, tcol, gout * inv[:, None], reduce="sum", plan=K.CsrPlan(trp, chunk_edges=4096))
+    assert (d_wh - want).abs().max().item() <= 2e-5 * max(want.abs().max().item(), 1.0)
+    # the gradients of the (all-equal) scores sum to zero over each destination's edges: sum_i d_el[i] == -... is not
+    # size independent, but d_el + (A d_er-contributions) must be finite and d_el must vanish where deg <= 1
+    assert bool(torch.isfinite(d_el).all()) and bool(torch.isfinite(d_er).all())
+    assert d_el[deg <= 1].abs().max().item() <= 1e-5 * max(gout.abs().max().item() * wh.abs().max().item(), 1.0) * D
 
 
 def test_full_reddit_sampler_and_blocks(K, reddit):
