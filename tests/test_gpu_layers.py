@@ -593,3 +593,45 @@ def test_graphed_training_step_equals_eager_epoch(nn, optimizer):
     assert c["n_batches"] == 6 and np.isfinite(c["loss"])
     with pytest.raises(ValueError):
         tr.load(seeds[:600], pre[0][1])              # more seeds than the captured capacity
+
+
+def test_graphed_training_step_with_per_batch_feature_rows(nn):
+    """The partitioned case: the input layer's source rows arrive per mini-batch (fetched from the owning GPUs) instead
+    of being read from a resident table.  Same update as the eager ``model(blocks, x)`` step."""
+    import copy
+    from dgll_b200 import graphs as G, ops, train as T
+    N, F = 20000, 64
+    rp, col = G.rmat_csr(N, N * 20, seed=5, device="cuda")
+    table = torch.randn((N, F), device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    labels = torch.randint(0, 5, (N,), device="cuda", generator=gen)
+    seeds = torch.randperm(N, device="cuda", generator=gen)[:256 * 4]
+    torch.manual_seed(1)
+    m1 = nn.GraphSAGE(F, 32, 5, 2, torch.relu, 0.0).cuda()
+    m2 = copy.deepcopy(m1)
+    o1 = torch.optim.SGD(m1.parameters(), lr=0.05)
+    o2 = torch.optim.SGD(m2.parameters(), lr=0.05)
+    pre = T.make_batches(rp, col, seeds, (8, 4), 256, rng_seed=2)
+    items = [(s, blocks, table[blocks[0].src_ids]) for s, blocks in pre]
+    prev = ops.get_gemm_precision()
+    ops.set_gemm_precision("fp32")
+    try:
+        m1.train()
+        losses = []
+        for s, blocks, x in items:
+            loss = torch.nn.functional.cross_entropy(m1(blocks, x), labels[s])
+            o1.zero_grad(set_to_none=True)
+            loss.backward()
+            o1.step()
+            losses.append(loss.item())
+        tr = T.GraphedSageTrainer(m2, o2, None, labels, 256, (8, 4), n_feat=F, precision="fp32")
+        tr.load(*items[0])
+        tr.capture()
+        r = tr.epoch(iter(items))                      # iterator => production overlapped with the replay
+    finally:
+        ops.set_gemm_precision(prev)
+    assert r["n_batches"] == 4 and abs(r["loss"] - sum(losses) / 4) <= 1e-5 * abs(sum(losses) / 4)
+    for p, q in zip(m1.parameters(), m2.parameters()):
+        assert rel_err(q.detach().cpu().numpy(), p.detach().cpu().numpy()) <= 2e-5
+    with pytest.raises(ValueError):
+        tr.load(items[0][0], items[0][1])              # feature rows are mandatory in this mode
