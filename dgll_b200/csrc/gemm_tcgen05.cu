@@ -374,13 +374,21 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
         if ((rc = make_tmap(&ta, Ab, M, Kp)) != DGLLB_OK) break;
         if ((rc = make_tmap(&tb, Bb, N, Kp)) != DGLLB_OK) break;
         const size_t smem = static_cast<size_t>(kStages) * (kStageBytesA + kStageBytesB) + 1024;
-        static std::once_flag attr_once;
-        static cudaError_t attr_err = cudaSuccess;
-        std::call_once(attr_once, [&]() {
-            attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem));
+        // the opt-in shared-memory size is a per-device function attribute: set it once per device, not per call
+        static std::once_flag attr_once[64];
+        static cudaError_t attr_err[64];
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        const int slot = dev_id & 63;
+        std::call_once(attr_once[slot], [&]() {
+            attr_err[slot] = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  static_cast<int>(smem));
         });
-        if (attr_err != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(attr_err)); rc = DGLLB_ERR_CUDA; break; }
+        if (attr_err[slot] != cudaSuccess) {
+            set_error("gemm: %s", cudaGetErrorString(attr_err[slot]));
+            rc = DGLLB_ERR_CUDA;
+            break;
+        }
         dim3 grid(static_cast<unsigned>((M + kBM - 1) / kBM), static_cast<unsigned>((N + kBN - 1) / kBN), 1);
         if (grid.y > 65535u) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: N too large"); break; }
         // split-K when the output has too few tiles to occupy the SMs and the reduction is long (dW = X^T G of a
