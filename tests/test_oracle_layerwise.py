@@ -72,3 +72,30 @@ def test_wrs_estimator_known_answer():
     assert np.array_equal(w, g["w"])
     np.random.seed(int(g["np_seed"]))
     assert np.array_equal(np.random.choice(len(g["p"]), int(g["m"]), False, g["p"]), g["idx"])
+
+
+def test_restatement_equals_the_scipy_pipeline_on_a_larger_graph():
+    """Independent of the fixtures: the plain-CSR restatement against the scipy calls the scripts make
+    (``lap[rows, :]``, ``Q.multiply(Q).sum(0)``, ``Q[:, picks].multiply(w).tocsr()``) on a 3,000-node graph, same
+    numpy stream — picks, block structure and values identical."""
+    sp = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(12)
+    n = 3000
+    src = rng.integers(0, n, 40000)
+    dst = (src + 1 + rng.zipf(1.4, 40000) % (n - 1)) % n
+    a = sp.coo_matrix((np.ones(40000), (src, dst)), shape=(n, n)).tocsr()
+    a.data[:] = 1.0
+    a = ((a + a.T) > 0).astype(np.float64).tocsr()
+    a.sort_indices()
+    lap = LW.laplacian(a.indptr.astype(np.int64), a.indices.astype(np.int64), "row")
+    lap_sp = sp.csr_matrix((lap[2], lap[1], lap[0]), shape=(n, n))
+    batch = rng.choice(n, 200, replace=False)
+    for flat in (False, True):
+        np.random.seed(5)
+        want = LW.scipy_ladies_batch(lap_sp, batch, [128, 256], flat=flat)
+        np.random.seed(5)
+        got = LW.layerwise_sample(lap, batch, [128, 256], "ladies", flat=flat)
+        for (w_ptr, w_idx, w_val, w_picks), g in zip(want, got):
+            assert np.array_equal(g["picks"], w_picks)
+            assert np.array_equal(g["indptr"], w_ptr) and np.array_equal(g["indices"], w_idx)
+            assert np.array_equal(g["data"], w_val)
