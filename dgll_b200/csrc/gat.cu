@@ -213,7 +213,8 @@ gat_forward_kernel(const GatParams p) {
 // Per 32-edge chunk: lane e scores edge e for every head (er[col] fetched as one vector), the chunk's softmax
 // statistics are 2 warp reductions per head, scores and column ids are parked in shared memory and every lane reads
 // back the weight of ITS head with a broadcast LDS.  Column ids / er values of the next chunks are prefetched.
-constexpr int kRowWarps = 8;
+// Launched with WARPS warps per block (template parameter): 1 by default — a block's registers are released when its
+// slowest row finishes, so one-warp blocks retire evenly on ragged rows (profiles/r01_block_size.md).
 
 // HEAVY = false: warp w owns row w (rows longer than p.chunk edges are skipped when a plan is given).
 // HEAVY = true : warp w owns plan item w = (row, k): edges [k*chunk, (k+1)*chunk) of a long row; it writes its partial
