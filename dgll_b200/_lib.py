@@ -50,6 +50,8 @@ SIGNATURES = {
     "dgllb_bin_spmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _L, _I, _I, _P, _P]),
     "dgllb_sample_neighbors": (_I, [_P, _I, _P, _P, _I, _L, _I, c_uint64, _P, _P, _P]),
     "dgllb_build_block": (_I, [_P, _L, _P, _P, _L, _P, _P, _P, _P]),
+    "dgllb_sample_neighbors_cap": (_I, [_P, _I, _P, _P, _I, _L, _I, c_uint64, _P, _P, _P, _P]),
+    "dgllb_build_block_cap": (_I, [_P, _L, _P, _P, _L, _I, _P, _P, _P, _P]),
     "dgllb_csr_slice_rows_ptr": (_I, [_P, _I, _P, _L, _P, _P]),
     "dgllb_csr_slice_rows_fill": (_I, [_P, _I, _P, _P, _P, _L, _P, _P, _P, _P]),
     "dgllb_col_sqsum": (_I, [_P, _P, _L, _L, _I, _P, _P, _P, _P]),

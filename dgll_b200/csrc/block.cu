@@ -32,6 +32,7 @@ __global__ void block_insert_kernel(const long long* __restrict__ dst_ids, const
     for (long long pos = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pos < total;
          pos += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long id = block_id_at(dst_ids, nbr, n_dst, pos);
+        if (id < 0) continue;  // padding slot of a fixed-capacity dst array
         unsigned slot = hash64(id, mask);
         while (true) {
             const long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
@@ -58,8 +59,11 @@ __global__ void block_flag_kernel(const long long* __restrict__ dst_ids, const i
          pos += static_cast<long long>(gridDim.x) * blockDim.x) {
         int f = 0, mp = 0;
         if (pos < total) {
-            mp = block_lookup(keys, minpos, mask, block_id_at(dst_ids, nbr, n_dst, pos));
-            f = mp == static_cast<int>(pos);
+            const long long id = block_id_at(dst_ids, nbr, n_dst, pos);
+            if (id >= 0) {
+                mp = block_lookup(keys, minpos, mask, id);
+                f = mp == static_cast<int>(pos);
+            }
         }
         flags[pos] = f;
         first_of[pos] = mp;
@@ -70,16 +74,26 @@ __global__ void block_emit_kernel(const long long* __restrict__ dst_ids, const i
                                   const int* __restrict__ row_ptr, long long n_dst, long long cap,
                                   const int* __restrict__ flags, const int* __restrict__ rank,
                                   const int* __restrict__ first_of, long long* __restrict__ src_ids,
-                                  int* __restrict__ col_local, int* __restrict__ counts_out) {
+                                  int* __restrict__ col_local, int* __restrict__ counts_out, int col_pad,
+                                  int n_counts) {
     const long long nnz = row_ptr[n_dst];
     const long long total = n_dst + nnz;
-    for (long long pos = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pos < total;
+    const long long limit = col_pad >= 0 ? cap : total;   // capacity mode also fills the unused edge slots
+    if (total == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < n_counts; ++k) counts_out[k] = 0;
+    for (long long pos = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pos < limit;
          pos += static_cast<long long>(gridDim.x) * blockDim.x) {
+        if (pos >= total) {
+            col_local[pos - n_dst] = col_pad;
+            continue;
+        }
         if (flags[pos]) src_ids[rank[pos]] = block_id_at(dst_ids, nbr, n_dst, pos);
         if (pos >= n_dst) col_local[pos - n_dst] = rank[first_of[pos]];
         if (pos == total - 1) {
             counts_out[0] = rank[pos] + flags[pos];  // num_src
             counts_out[1] = static_cast<int>(nnz);
+            // valid (non-negative) dst ids come first and are unique: each is its own first occurrence
+            if (n_counts > 2) counts_out[2] = n_dst < total ? rank[n_dst] : rank[pos] + flags[pos];
         }
     }
 }
@@ -88,9 +102,9 @@ __global__ void block_emit_kernel(const long long* __restrict__ dst_ids, const i
 
 using namespace dgllb;
 
-extern "C" int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const int32_t* row_ptr,
-                                 const int32_t* nbr_global, int64_t nnz_cap, int64_t* src_ids, int32_t* col_local,
-                                 int32_t* counts_out, void* stream) {
+static int build_block_impl(const int64_t* dst_ids, int64_t n_dst, const int32_t* row_ptr, const int32_t* nbr_global,
+                            int64_t nnz_cap, int64_t* src_ids, int32_t* col_local, int32_t* counts_out, int col_pad,
+                            int n_counts, void* stream) {
     DGLLB_REQUIRE(n_dst >= 0 && nnz_cap >= 0, "build_block: negative size");
     DGLLB_REQUIRE(n_dst + nnz_cap < (1ll << 30), "build_block: block too large for 32-bit positions");
     DGLLB_REQUIRE(row_ptr && src_ids && counts_out && (n_dst == 0 || dst_ids) && (nnz_cap == 0 || (nbr_global && col_local)),
@@ -101,7 +115,7 @@ extern "C" int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const in
     if (rc != DGLLB_OK) return rc;
     const long long cap = n_dst + nnz_cap;
     if (cap == 0) {
-        DGLLB_CUDA_TRY(cudaMemsetAsync(counts_out, 0, 2 * sizeof(int), st));
+        DGLLB_CUDA_TRY(cudaMemsetAsync(counts_out, 0, n_counts * sizeof(int), st));
         return DGLLB_OK;
     }
     unsigned tsize = 1024;
@@ -123,6 +137,8 @@ extern "C" int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const in
     do {
         cudaError_t e = cudaMemsetAsync(keys, 0xFF, sizeof(long long) * tsize, st);      // all keys = -1
         if (e == cudaSuccess) e = cudaMemsetAsync(minpos, 0x7F, sizeof(int) * tsize, st); // large positive
+        if (e == cudaSuccess && n_counts > 2)   // capacity mode: unused src slots read as padding (-1) downstream
+            e = cudaMemsetAsync(src_ids, 0xFF, sizeof(long long) * cap, st);
         if (e != cudaSuccess) { set_error("build_block: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
         const int tb = 256;
         long long blocks = (cap + tb - 1) / tb;
@@ -136,11 +152,25 @@ extern "C" int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const in
         if (e != cudaSuccess) { set_error("build_block: scan: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
         block_emit_kernel<<<g, tb, 0, st>>>(reinterpret_cast<const long long*>(dst_ids), nbr_global, row_ptr, n_dst, cap,
                                             flags, rank, first_of, reinterpret_cast<long long*>(src_ids), col_local,
-                                            counts_out);
+                                            counts_out, col_pad, n_counts);
         g_launch_count.fetch_add(4);
         e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("build_block: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
     } while (0);
     cudaFreeAsync(ws, st);
     return rc;
+}
+
+extern "C" int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const int32_t* row_ptr,
+                                 const int32_t* nbr_global, int64_t nnz_cap, int64_t* src_ids, int32_t* col_local,
+                                 int32_t* counts_out, void* stream) {
+    return build_block_impl(dst_ids, n_dst, row_ptr, nbr_global, nnz_cap, src_ids, col_local, counts_out, -1, 2, stream);
+}
+
+extern "C" int dgllb_build_block_cap(const int64_t* dst_ids, int64_t n_dst_cap, const int32_t* row_ptr,
+                                     const int32_t* nbr_global, int64_t nnz_cap, int col_pad, int64_t* src_ids,
+                                     int32_t* col_local, int32_t* counts_out, void* stream) {
+    DGLLB_REQUIRE(col_pad >= 0, "build_block_cap: col_pad must be >= 0 (the padding column id of the consumer)");
+    return build_block_impl(dst_ids, n_dst_cap, row_ptr, nbr_global, nnz_cap, src_ids, col_local, counts_out, col_pad, 3,
+                            stream);
 }

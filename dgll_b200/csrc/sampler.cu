@@ -40,18 +40,21 @@ __global__ void sample_count_kernel(const void* row_ptr, int rp64, const void* s
     if (i > n_seeds) return;
     if (i == n_seeds) { counts[i] = 0; return; }
     const long long v = smp_seed(seeds, s64, i);
+    if (v < 0) { counts[i] = 0; return; }  // padding slot of a fixed-capacity seed array
     const long long deg = smp_rp(row_ptr, rp64, v + 1) - smp_rp(row_ptr, rp64, v);
     counts[i] = static_cast<int>(fanout < 0 ? deg : min(deg, static_cast<long long>(fanout)));
 }
 
 __global__ void __launch_bounds__(256)
 sample_fill_kernel(const void* row_ptr, int rp64, const int* __restrict__ col, const void* seeds, int s64,
-                   long long n_seeds, int fanout, uint64_t rng_seed, const int* __restrict__ out_row_ptr,
-                   int* __restrict__ out_col) {
+                   long long n_seeds, int fanout, uint64_t rng_seed, const unsigned long long* __restrict__ rng_offset,
+                   const int* __restrict__ out_row_ptr, int* __restrict__ out_col) {
     const int lane = threadIdx.x & 31;
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_seeds) return;
     const long long v = smp_seed(seeds, s64, i);
+    if (v < 0) return;                       // padding slot
+    if (rng_offset) rng_seed += *rng_offset; // per-replay offset kept in device memory (CUDA-graph friendly)
     const long long beg = smp_rp(row_ptr, rp64, v), deg = smp_rp(row_ptr, rp64, v + 1) - beg;
     const long long ob = out_row_ptr[i];
     if (fanout < 0 || deg <= fanout) {
@@ -83,10 +86,10 @@ sample_fill_kernel(const void* row_ptr, int rp64, const int* __restrict__ col, c
 
 using namespace dgllb;
 
-extern "C" int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
-                                      const void* seeds, int seeds_is64, int64_t n_seeds, int fanout,
-                                      uint64_t rng_seed, int32_t* out_row_ptr, int32_t* out_col,
-                                      void* stream) {
+static int sample_neighbors_impl(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx, const void* seeds,
+                                 int seeds_is64, int64_t n_seeds, int fanout, uint64_t rng_seed,
+                                 const unsigned long long* rng_offset, int32_t* out_row_ptr, int32_t* out_col,
+                                 void* stream) {
     DGLLB_REQUIRE(n_seeds >= 0, "sample_neighbors: negative n_seeds");
     DGLLB_REQUIRE(row_ptr && out_row_ptr && (n_seeds == 0 || seeds), "sample_neighbors: null pointer");
     if (fanout > 32) {
@@ -116,7 +119,8 @@ extern "C" int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, con
         if (n_seeds > 0 && out_col) {
             const long long blocks = (n_seeds * 32 + tb - 1) / tb;
             sample_fill_kernel<<<static_cast<unsigned>(blocks), tb, 0, st>>>(
-                row_ptr, row_ptr_is64, col_idx, seeds, seeds_is64, n_seeds, fanout, rng_seed, out_row_ptr, out_col);
+                row_ptr, row_ptr_is64, col_idx, seeds, seeds_is64, n_seeds, fanout, rng_seed, rng_offset, out_row_ptr,
+                out_col);
             g_launch_count.fetch_add(1);
         }
         e = cudaGetLastError();
@@ -124,4 +128,20 @@ extern "C" int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, con
     } while (0);
     cudaFreeAsync(ws, st);
     return rc;
+}
+
+extern "C" int dgllb_sample_neighbors(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                                      const void* seeds, int seeds_is64, int64_t n_seeds, int fanout,
+                                      uint64_t rng_seed, int32_t* out_row_ptr, int32_t* out_col,
+                                      void* stream) {
+    return sample_neighbors_impl(row_ptr, row_ptr_is64, col_idx, seeds, seeds_is64, n_seeds, fanout, rng_seed, nullptr,
+                                 out_row_ptr, out_col, stream);
+}
+
+extern "C" int dgllb_sample_neighbors_cap(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                                          const void* seeds, int seeds_is64, int64_t n_seeds_cap, int fanout,
+                                          uint64_t rng_seed, const uint64_t* rng_offset, int32_t* out_row_ptr,
+                                          int32_t* out_col, void* stream) {
+    return sample_neighbors_impl(row_ptr, row_ptr_is64, col_idx, seeds, seeds_is64, n_seeds_cap, fanout, rng_seed,
+                                 reinterpret_cast<const unsigned long long*>(rng_offset), out_row_ptr, out_col, stream);
 }

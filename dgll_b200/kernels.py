@@ -541,6 +541,54 @@ def csr_select_cols(q_row_ptr, q_col, q_values, pos, scale=None, with_values=Tru
     return out_rp, out_col, out_val
 
 
+def sample_neighbors_cap(row_ptr, col_idx, seeds, fanout, rng_seed=0, rng_offset=None, out_row_ptr=None, out_col=None):
+    """Fixed-capacity ``sample_neighbors``: negative entries of ``seeds`` are padding slots (degree-0 rows), the random
+    seed is ``rng_seed + rng_offset[0]`` with ``rng_offset`` a uint64/int64 device scalar.  No size is read back:
+    returns (row_ptr int32[n+1], col int32[n*fanout]); the true nnz is row_ptr[-1] on the device."""
+    _need_cuda(row_ptr, col_idx, seeds, rng_offset, out_row_ptr, out_col)
+    rp, is64 = _rowptr(row_ptr)
+    col = _index32(col_idx, "col_idx")
+    if seeds.dtype not in (torch.int32, torch.int64) or not seeds.is_contiguous():
+        raise TypeError("seeds must be a contiguous int32/int64 tensor")
+    if fanout is None or fanout < 0:
+        raise ValueError("sample_neighbors_cap needs a fixed fanout (the output capacity is n * fanout)")
+    n, dev = seeds.numel(), rp.device
+    if out_row_ptr is None:
+        out_row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    if out_col is None:
+        out_col = torch.empty(max(n * int(fanout), 1), dtype=torch.int32, device=dev)
+    if out_row_ptr.numel() != n + 1 or out_col.numel() < n * int(fanout):
+        raise ValueError("sample_neighbors_cap: output buffers too small")
+    check(lib().dgllb_sample_neighbors_cap(_p(rp), is64, _p(col), _p(seeds), int(seeds.dtype == torch.int64), n,
+                                           int(fanout), ctypes.c_uint64(rng_seed & 0xFFFFFFFFFFFFFFFF), _p(rng_offset),
+                                           _p(out_row_ptr), _p(out_col), _stream()), "sample_neighbors_cap")
+    return out_row_ptr, out_col
+
+
+def build_block_cap(dst_ids, row_ptr, nbr_global, col_pad, src_ids=None, col_local=None, counts=None):
+    """Fixed-capacity ``build_block``: negative ``dst_ids`` are padding; ``src_ids`` comes back -1 padded (usable as the
+    next layer's seed array as it is), unused ``col_local`` slots = ``col_pad``; counts int32[3] on the device =
+    {num_src, nnz, n_dst_valid}.  Nothing is read back."""
+    _need_cuda(dst_ids, row_ptr, nbr_global, src_ids, col_local, counts)
+    if dst_ids.dtype != torch.int64 or not dst_ids.is_contiguous():
+        raise TypeError("build_block_cap: dst_ids must be a contiguous int64 tensor")
+    if row_ptr.dtype != torch.int32 or not row_ptr.is_contiguous():
+        raise TypeError("build_block_cap: row_ptr must be int32 (output of sample_neighbors_cap)")
+    nbr = _index32(nbr_global, "nbr_global")
+    n_dst, cap, dev = dst_ids.numel(), nbr.numel(), dst_ids.device
+    if src_ids is None:
+        src_ids = torch.empty(n_dst + cap, dtype=torch.int64, device=dev)
+    if col_local is None:
+        col_local = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    if counts is None:
+        counts = torch.empty(3, dtype=torch.int32, device=dev)
+    if src_ids.numel() < n_dst + cap or col_local.numel() < cap or counts.numel() < 3:
+        raise ValueError("build_block_cap: output buffers too small")
+    check(lib().dgllb_build_block_cap(_p(dst_ids), n_dst, _p(row_ptr), _p(nbr), cap, int(col_pad), _p(src_ids),
+                                      _p(col_local), _p(counts), _stream()), "build_block_cap")
+    return src_ids, col_local, counts
+
+
 def gcn_fused_forward_v2(row_ptr, col_idx, values, X, W, num_neighbors, actual_F):
     _need_cuda(row_ptr, col_idx, values, X, W, num_neighbors)
     N, Fp, Hd = X.size(0), X.size(1), W.size(1)

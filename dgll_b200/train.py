@@ -141,6 +141,72 @@ class GraphedSageTrainer:
         world = parallel.dist.get_world_size(group) if parallel.dist.is_initialized() else 1
         self._opt_in_graph = world == 1 and bool(opt.defaults.get("capturable", False))
 
+    # ---- sampler inside the graph (fixed-capacity sampler + block builder, no size read-backs) ------------------
+    def enable_device_sampler(self, row_ptr, col_idx, rng_seed=0):
+        """Put the neighbour sampler and the block builder INSIDE the captured step (resident-table mode): one graph
+        launch per mini-batch, nothing read back.  Uses the fixed-capacity kernels (``dgllb_sample_neighbors_cap`` /
+        ``dgllb_build_block_cap``: negative ids are padding, unused edge slots hold the padding column) writing straight
+        into the capture buffers; the random seed lives in device memory and is bumped by the graph itself, following
+        the same schedule as ``sage_epoch(..., rng_seed=)`` / ``graphs.sample_blocks`` so the two draw identical blocks.
+        Call before ``capture()``; then drive with ``step_sampled(seeds)`` / ``epoch_sampled(seeds)``."""
+        if self.x is not None:
+            raise ValueError("device sampler in the graph: resident-table mode only")
+        dev = self.seeds.device
+        self._smp = (row_ptr, col_idx)
+        self._rng_base = int(rng_seed) * 7919 * 1000003           # (rng_seed*7919 + b)*1000003 + layer, b via the offset
+        self._rng_off = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._nbr1 = torch.zeros(self.cap_e1, dtype=torch.int32, device=dev)     # global ids of block1's neighbours
+        self._src1 = torch.full((self.cap_d0,), -1, dtype=torch.int64, device=dev)
+        self._cnt1 = torch.zeros(3, dtype=torch.int32, device=dev)
+        self.graph = None
+
+    def _sample_into_buffers(self):
+        from . import kernels as K
+        rp, col = self._smp
+        f0, f1 = self.cap_e0 // self.cap_d0, self.cap_e1 // self.B
+        K.sample_neighbors_cap(rp, col, self.seeds, f1, rng_seed=self._rng_base, rng_offset=self._rng_off,
+                               out_row_ptr=self.rp1, out_col=self._nbr1)
+        K.build_block_cap(self.seeds, self.rp1, self._nbr1, col_pad=self.cap_d0, src_ids=self._src1, col_local=self.col1,
+                          counts=self._cnt1)
+        K.sample_neighbors_cap(rp, col, self._src1, f0, rng_seed=self._rng_base + 1, rng_offset=self._rng_off,
+                               out_row_ptr=self.rp0, out_col=self.col0)
+        torch.clamp(self._src1, min=0, out=self.ids0)            # padding rows gather row 0 (their output is unused)
+        self.valid.copy_(self.seeds >= 0)
+        self._rng_off += 1000003
+
+    def step_sampled(self, seeds):
+        """One training step on ``seeds`` (<= batch_size ids) with the sampler inside the replayed graph."""
+        ns = seeds.numel()
+        if ns > self.B:
+            raise ValueError("GraphedSageTrainer: more seeds than the captured batch size")
+        self.seeds[:ns].copy_(seeds)
+        if ns < self.B:
+            self.seeds[ns:].fill_(-1)
+        self.step()
+
+    def epoch_sampled(self, seeds, first_batch=0):
+        """One epoch over ``seeds`` in batches of ``batch_size``; the in-graph RNG offset is set so that batch b draws
+        what ``sage_epoch`` draws for it."""
+        if getattr(self, "_smp", None) is None:
+            raise ValueError("call enable_device_sampler(row_ptr, col_idx) first")
+        if self.graph is None:
+            self.seeds.copy_(torch.nn.functional.pad(seeds[:self.B], (0, max(0, self.B - seeds[:self.B].numel())), value=-1))
+            self.capture()
+        self._rng_off.fill_(first_batch * 1000003)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter()
+        self.loss_sum.zero_()
+        e0.record()
+        n = 0
+        for i in range(0, seeds.numel(), self.B):
+            self.step_sampled(seeds[i:i + self.B])
+            n += 1
+        e1.record()
+        torch.cuda.synchronize()
+        return {"time_s": e0.elapsed_time(e1) * 1e-3, "wall_s": time.perf_counter() - t_wall, "n_batches": n,
+                "loss": float(self.loss_sum.item()) / max(n, 1)}
+
     def _blocks(self):
         b0 = G.Block(self.rp0, self.col0, self.col0, self.ids0 if self.x is None else self._src_shape, self.cap_d0)
         b1 = G.Block(self.rp1, self.col1, self.col1, self.ids0, self.B)
@@ -177,11 +243,13 @@ class GraphedSageTrainer:
         self.col1[e1:].fill_(self.cap_d0)
 
     def _step_body(self):
+        if getattr(self, "_smp", None) is not None:
+            self._sample_into_buffers()
         if self.x is None:
             logits = self.model(self._blocks(), None, feat_table=self.table)
         else:
             logits = self.model(self._blocks(), self.x)
-        target = torch.where(self.valid, self.labels[self.seeds], torch.full_like(self.seeds, -100))
+        target = torch.where(self.valid, self.labels[self.seeds.clamp(min=0)], torch.full_like(self.seeds, -100))
         loss = torch.nn.functional.cross_entropy(logits, target, ignore_index=-100)
         loss.backward()
         self.loss.copy_(loss.detach())

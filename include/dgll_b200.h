@@ -341,6 +341,24 @@ int dgllb_build_block(const int64_t* dst_ids, int64_t n_dst, const int32_t* row_
                       const int32_t* nbr_global, int64_t nnz_cap, int64_t* src_ids, int32_t* col_local,
                       int32_t* counts_out, void* stream);
 
+/*
+ * Fixed-capacity variants for pipelines that must not read sizes back (CUDA-graph capture of sampler + block builder +
+ * training step).  Convention: a NEGATIVE id is a padding slot.
+ *   dgllb_sample_neighbors_cap: seeds[n_seeds_cap] may end in -1 entries (degree 0 rows); the effective random seed is
+ *     rng_seed + *rng_offset (device memory, may be NULL), so a replayed graph draws new samples when a tiny kernel bumps
+ *     the offset.
+ *   dgllb_build_block_cap: dst_ids[n_dst_cap] may end in -1 entries; src_ids is pre-filled with -1 (so it can be the next
+ *     layer's padded seed array as it is), unused slots of col_local[nnz_cap] are set to col_pad (the padding column id of
+ *     the consumer, e.g. the n_cols that dgllb_csr_transpose drops), counts_out int32[3] = {num_src, nnz, n_dst_valid}.
+ */
+int dgllb_sample_neighbors_cap(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                               const void* seeds, int seeds_is64, int64_t n_seeds_cap, int fanout,
+                               uint64_t rng_seed, const uint64_t* rng_offset, int32_t* out_row_ptr,
+                               int32_t* out_col, void* stream);
+int dgllb_build_block_cap(const int64_t* dst_ids, int64_t n_dst_cap, const int32_t* row_ptr,
+                          const int32_t* nbr_global, int64_t nnz_cap, int col_pad, int64_t* src_ids,
+                          int32_t* col_local, int32_t* counts_out, void* stream);
+
 /* ------------------------------------------- layer-wise importance sampling -- */
 
 /*
