@@ -109,7 +109,7 @@ class GraphedSageTrainer:
     the all-reduce) run eagerly after the replay."""
 
     def __init__(self, model, opt, table, labels, batch_size=1024, fanouts=(25, 10), group=None, precision=None,
-                 n_feat=None):
+                 n_feat=None, capture_collectives=False):
         if len(fanouts) != 2 or len(model.layers) != 2:
             raise ValueError("GraphedSageTrainer: 2-layer models / two fanouts")
         if table is None and n_feat is None:
@@ -140,6 +140,20 @@ class GraphedSageTrainer:
         self._precision = precision
         world = parallel.dist.get_world_size(group) if parallel.dist.is_initialized() else 1
         self._opt_in_graph = world == 1 and bool(opt.defaults.get("capturable", False))
+        # DRAFT (round 2): with more than one rank, capture the gradient all-reduce (NCCL is graph-capturable) and the
+        # optimizer too.  Gradients live in ONE flat buffer (p.grad are views): zeroed, accumulated into by autograd,
+        # all-reduced in place; the 1/world average is folded into the loss scale.  One launch per step on every rank.
+        self._world = world
+        self._flat = None
+        if capture_collectives and world > 1:
+            if not opt.defaults.get("capturable", False):
+                raise ValueError("capture_collectives needs a capturable optimizer")
+            self._flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+            off = 0
+            for p in self.params:
+                p.grad = self._flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._opt_in_graph = True
 
     # ---- sampler inside the graph (fixed-capacity sampler + block builder, no size read-backs) ------------------
     def enable_device_sampler(self, row_ptr, col_idx, rng_seed=0):
@@ -251,7 +265,12 @@ class GraphedSageTrainer:
             logits = self.model(self._blocks(), self.x)
         target = torch.where(self.valid, self.labels[self.seeds.clamp(min=0)], torch.full_like(self.seeds, -100))
         loss = torch.nn.functional.cross_entropy(logits, target, ignore_index=-100)
-        loss.backward()
+        if self._flat is not None:
+            self._flat.zero_()
+            (loss / self._world).backward()                     # accumulates into the views of the flat buffer
+            parallel.dist.all_reduce(self._flat, op=parallel.dist.ReduceOp.SUM, group=self.group)
+        else:
+            loss.backward()
         self.loss.copy_(loss.detach())
         self.loss_sum += loss.detach()
         if self._opt_in_graph:
@@ -272,7 +291,8 @@ class GraphedSageTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                       # warm-up off the capture stream (allocator, lazy init)
             for _ in range(2):
-                self.opt.zero_grad(set_to_none=True)
+                if self._flat is None:
+                    self.opt.zero_grad(set_to_none=True)
                 self._step_body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -288,7 +308,8 @@ class GraphedSageTrainer:
                         else:
                             v.zero_()
         self.loss_sum.zero_()
-        self.opt.zero_grad(set_to_none=True)
+        if self._flat is None:
+            self.opt.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step_body()

@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph = the training step replayed as one CUDA graph on fixed-capacity buffers "
                          "(train.GraphedSageTrainer); eager = Python-dispatched step")
+    ap.add_argument("--capture-collectives", action="store_true",
+                    help="DRAFT (round 2): capture the flat gradient all-reduce and Adam inside the step graph (N > 1)")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="graph mode: produce step i+1 (sample, build blocks, fetch rows) on the main stream instead of a "
                          "side stream that runs under the replay of step i")
@@ -86,14 +88,16 @@ def main():
     hx = P.PeerShardedTable(N, table) if args.halo == "peer" else P.HaloExchange(N, table)
     torch.manual_seed(0)
     model = dnn.GraphSAGE(F, hidden, C, 2, torch.relu, 0.0).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=(world == 1 and args.mode == "graph"))
+    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True,
+                           capturable=((world == 1 or args.capture_collectives) and args.mode == "graph"))
     params = list(model.parameters())
     ops.set_gemm_precision(args.precision)
     fetch = (lambda ids: hx.fetch_padded(ids)) if args.halo == "padded" else (lambda ids: hx.fetch(ids))
     trainer, mode, mode_err = None, args.mode, None
     if args.mode == "graph":
         try:
-            trainer = T.GraphedSageTrainer(model, opt, None, labels, args.batch, fanouts, n_feat=F)
+            trainer = T.GraphedSageTrainer(model, opt, None, labels, args.batch, fanouts, n_feat=F,
+                                           capture_collectives=args.capture_collectives)
             b0 = G.sample_blocks(row_ptr, col, seeds_all[:args.batch], fanouts, rng_seed=999 + rank)
             trainer.load(seeds_all[:args.batch], b0, fetch(b0[0].src_ids))
             trainer.capture()
