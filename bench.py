@@ -5,19 +5,28 @@ Workload (config.workload): GraphSAGE-mean 2-layer, fanout 25/10, batch 1,024 se
 Reddit-shaped graph (N=232,965, nnz=114,615,892, F=602 fp32, row stride 604).  One STEP = the neighbourhood
 aggregation path of one mini-batch with pre-sampled blocks resident in HBM:
     layer 0: mean-aggregate block0 straight from the feature table (the sampled-block feature gather is fused
-             into the aggregation: col ids are global), F=602      -> [n_dst0, 602]
+             into the aggregation: col ids are global), F=602      -> [n_dst0, 602] (row stride 604)
              + TMA row gather of the dst (self) rows                -> [n_dst0, 604]
     layer 1: mean-aggregate block1 over the hidden rows, F=256      -> [1024, 256]
 ``value`` = algorithmic bytes of those kernels (SURVEY.md §8 d formulas) / step time, whole job, GB/s.
 ``e2e``   = the same metric through the public API with the blocks in pinned HOST memory: H2D of the block
             arrays + the kernels + D2H of the layer-1 aggregate, all inside the timed region.
-``roofline`` = the dominant kernel (layer-0 SpMM) timed with CUDA events on its own stream, inside the timed region.
+``roofline`` = the dominant kernel (layer-0 SpMM) timed with CUDA events on its own stream, inside the timed region;
+            ``frac`` on algorithmic bytes, ``dram_frac`` on the DRAM bytes ncu measured for the same launch.
 ``cpu_baseline`` / ``--impl reference`` = the reference's CPU aggregation (torch.sparse.mm on a COO block, as
             dgll/nn/Convolution/gcnconv.py:31 / Evaluation/PPI/gcn_model.py:76 do) and a best-effort CSR port
-            (oracle/oracle.c, OpenMP) on the same blocks, all host threads.
-Multi-GPU (--gpus N under torchrun): the batch axis shards — every rank holds the graph + features and runs its own
-mini-batches (the reference's data-parallel scheme, GPU Accelerator/MQGCN.py:94-157); no data-path collective;
-scaling = weak.
+            (oracle/oracle.c, OpenMP) on THE SAME seeded blocks and feature table, all host threads.
+``gpu_baseline`` = the library call behind the reference's layers on the same box and inputs: torch.sparse.mm on a
+            CUDA CSR matrix (cuSPARSE).
+Extras (do not change ``value``):
+  ``bf16_table``   the same step with the feature table stored in bf16 (row stride 608): half the bytes per edge.
+  ``epoch``        sampled-GraphSAGE TRAINING epoch on the Reddit-shaped graph (second half of BASELINE's metric).
+  ``partitioned``  BASELINE configs[4]: papers100M-shaped R-MAT graph, features node-range partitioned over the N GPUs,
+                   one CUDA graph per mini-batch (dgll_b200.pipelined), halo rows read over NVLink by the aggregation
+                   kernel itself ("peer") and, for comparison, exchanged with NCCL all_to_all ("nccl").
+Multi-GPU (--gpus N under torchrun): the headline step shards over the batch axis — every rank holds the graph +
+features and runs its own mini-batches (the reference's data-parallel scheme, GPU Accelerator/MQGCN.py:94-157); no
+data-path collective; scaling = weak.  The partitioned extra is the path with a real exchange step.
 """
 import argparse
 import json
@@ -32,27 +41,33 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_NODES, NNZ, FEAT, HIDDEN = 232965, 114615892, 602, 256
+LD32, LD16 = 604, 608                       # row strides (elements) of the fp32 / bf16 feature table: 16-byte rows
 BATCH, FANOUTS = 1024, (25, 10)
 N_BATCHES = 16  # distinct pre-sampled mini-batches cycled through the timed steps
+NCU_SUMMARY = os.path.join("profiles", "r02_spmm_headline.txt")
+WORKLOAD = ("GraphSAGE-mean 2-layer fanout 25/10 batch 1024, aggregation path of one mini-batch, synthetic "
+            "Reddit-shaped graph N=232965 nnz=114615892 F=602 fp32")
+METRIC = "SpMM aggregation GB/s (algorithmic bytes, sampled GraphSAGE-mean blocks)"
 
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu summary
-    (profiles/r01_spmm_headline.txt, one `--set full` capture of the same command).  None when absent."""
-    path = os.path.join(ROOT, "profiles", "r01_spmm_headline.txt")
-    try:
-        rd = wr = None
-        for line in open(path):
-            f = line.split()
-            if len(f) >= 3 and f[0] == "dram__bytes_read.sum" and rd is None:
-                rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
-            if len(f) >= 3 and f[0] == "dram__bytes_write.sum" and wr is None:
-                wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
-            if rd is not None and wr is not None:
-                return rd + wr
-    except Exception:
-        pass
-    return None
+    (one `--set full` capture of the same command).  None when absent."""
+    for rel in (NCU_SUMMARY, os.path.join("profiles", "r01_spmm_headline.txt")):
+        path = os.path.join(ROOT, rel)
+        try:
+            rd = wr = None
+            for line in open(path):
+                f = line.split()
+                if len(f) >= 3 and f[0] == "dram__bytes_read.sum" and rd is None:
+                    rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+                if len(f) >= 3 and f[0] == "dram__bytes_write.sum" and wr is None:
+                    wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+                if rd is not None and wr is not None:
+                    return rd + wr, rel
+        except Exception:
+            pass
+    return None, None
 
 
 def peaks():
@@ -114,11 +129,39 @@ def alg_bytes_gather(m, row_bytes, id_bytes=8):
     return m * (id_bytes + 2 * row_bytes)
 
 
+def bench_config(world, n_dst0, nnz0):
+    """The ``config`` object — identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch": BATCH, "fanouts": list(FANOUTS), "hidden": HIDDEN,
+            "parallelism": "dp%d (batch axis; graph+features replicated)" % world,
+            "flush": "inputs larger than L2: 563 MB feature table, %d distinct mini-batches cycled" % N_BATCHES,
+            "block0": {"n_dst": n_dst0, "nnz": nnz0},
+            "inputs": "R-MAT graph + N(0,1) features + device-sampled blocks, all from seed 0 (same arrays in both arms)"}
+
+
+# ------------------------------------------------------------------ seeded inputs --
+def make_inputs(seed, rank, dev):
+    """Graph, feature table and the N_BATCHES sampled mini-batches of the workload, on ``dev``.  Both arms call this
+    with the same seed, so the CPU arm times the reference path on exactly the arrays the GPU arm aggregates."""
+    import torch
+    from dgll_b200 import graphs as G
+    row_ptr, col_idx = G.rmat_csr(N_NODES, NNZ, seed=seed, device=dev)
+    table = G.feature_table(N_NODES, FEAT, seed=seed, device=dev, pad_to=LD32)     # [N, 604] fp32, 563 MB > L2
+    gen = torch.Generator(device=dev).manual_seed(seed + 1000 * rank)
+    n_train = int(0.66 * N_NODES)
+    perm = torch.randperm(n_train, device=dev, generator=gen)
+    batches = []
+    for b in range(N_BATCHES):
+        seeds = perm[b * BATCH:(b + 1) * BATCH]
+        b0, b1 = G.sample_blocks(row_ptr, col_idx, seeds, FANOUTS, rng_seed=seed * 7919 + b + 131 * rank)
+        batches.append({"rp0": b0.row_ptr, "col0": b0.col_global, "dst0": b0.dst_ids.contiguous(), "n_dst0": b0.num_dst,
+                        "rp1": b1.row_ptr, "col1": b1.col, "n_dst1": b1.num_dst})
+    return row_ptr, col_idx, table, gen, batches
+
+
 # --------------------------------------------------------------------- CPU arm --
-def cpu_blocks(n_batches, seed=0):
-    """The same workload built on the host with numpy (uniform-degree control graph slice is NOT used: the blocks
-    are sampled from a host copy of a seeded random Reddit-shaped neighbourhood model): per mini-batch, block0 has
-    ~11K dst rows x 25 sampled neighbours over 232,965 feature rows of 602 floats; block1 1,024 x 10."""
+def numpy_blocks(n_batches, seed=0):
+    """Fallback inputs when no CUDA device is visible (CPU-only containers): uniform-random blocks of the workload's
+    shapes.  On the GPU box the CPU arm uses ``make_inputs`` instead — the same arrays as the GPU arm."""
     import numpy as np
     rng = np.random.default_rng(seed)
     out = []
@@ -135,37 +178,61 @@ def cpu_blocks(n_batches, seed=0):
     return out
 
 
+def host_inputs(seed, n_blocks):
+    """(x float32[N, 602] on the host, blocks, origin string) for the CPU arm."""
+    import numpy as np
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(0)
+            dev = torch.device("cuda", 0)
+            _, _, table, _, batches = make_inputs(seed, 0, dev)
+            x = table[:, :FEAT].contiguous().cpu().numpy()
+            blocks = [(bt["rp0"].cpu().numpy().astype(np.int64), bt["col0"].cpu().numpy().astype(np.int32),
+                       bt["dst0"].cpu().numpy().astype(np.int64), bt["rp1"].cpu().numpy().astype(np.int64),
+                       bt["col1"].cpu().numpy().astype(np.int32)) for bt in batches[:n_blocks]]
+            del table, batches
+            torch.cuda.empty_cache()
+            return x, blocks, "same seeded graph, feature table and sampled blocks as the GPU arm (generated on the device, copied to the host before timing)"
+    except Exception:
+        pass
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((N_NODES, FEAT), dtype=np.float32), numpy_blocks(n_blocks, seed),
+            "no CUDA device visible: numpy uniform-random blocks of the workload's shapes")
+
+
 def cpu_step_bytes(blk):
     rp0, col0, dst0, rp1, col1 = blk
-    return (alg_bytes_spmm(col0.size, rp0.size - 1, FEAT) + alg_bytes_gather(dst0.size, 604 * 4)
-            + alg_bytes_spmm(col1.size, rp1.size - 1, HIDDEN))
+    return (alg_bytes_spmm(col0.size, rp0.size - 1, FEAT, rp=4) + alg_bytes_gather(dst0.size, LD32 * 4)
+            + alg_bytes_spmm(col1.size, rp1.size - 1, HIDDEN, rp=4))
 
 
-def run_cpu_arm(steps, warmup, budget_s=25.0, which=("coo", "csr")):
+def run_cpu_arm(steps, warmup, budget_s=25.0, which=("coo", "csr"), seed=0, n_blocks=N_BATCHES):
     """Times the reference CPU aggregation on host cores.  Returns dict(value GB/s, per-variant numbers)."""
     import numpy as np
     import torch
     import oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal((N_NODES, FEAT), dtype=np.float32)
+    x, blocks, origin = host_inputs(seed, n_blocks)
     xt = torch.from_numpy(x)
-    h1 = rng.standard_normal((12000, HIDDEN), dtype=np.float32)
-    blocks = cpu_blocks(max(2, min(steps + warmup, 4)))
+    h1 = np.random.default_rng(seed).standard_normal((BATCH * (1 + FANOUTS[1]), HIDDEN), dtype=np.float32)
     res = {}
 
     def step_coo(blk):
+        # the reference rebuilds the COO adjacency inside every forward (Evaluation/PPI/gcn_model.py:68-76): timed
         rp0, col0, dst0, rp1, col1 = blk
         rows0 = torch.from_numpy(np.repeat(np.arange(rp0.size - 1), np.diff(rp0)))
+        deg0 = np.maximum(np.diff(rp0), 1).astype(np.float32)
         a0 = torch.sparse_coo_tensor(torch.stack([rows0, torch.from_numpy(col0).long()]),
-                                     torch.full((col0.size,), 1.0 / FANOUTS[0]), (rp0.size - 1, N_NODES))
+                                     torch.from_numpy(np.repeat(1.0 / deg0, np.diff(rp0))), (rp0.size - 1, N_NODES))
         agg0 = torch.sparse.mm(a0, xt)                       # gcnconv.py:31 / gcn_model.py:76
         self0 = xt[torch.from_numpy(dst0)]                   # dgraph.py:105 features[nodes]
         rows1 = torch.from_numpy(np.repeat(np.arange(rp1.size - 1), np.diff(rp1)))
+        deg1 = np.maximum(np.diff(rp1), 1).astype(np.float32)
         h = torch.from_numpy(h1[:rp0.size - 1])
         a1 = torch.sparse_coo_tensor(torch.stack([rows1, torch.from_numpy(col1).long()]),
-                                     torch.full((col1.size,), 1.0 / FANOUTS[1]), (rp1.size - 1, rp0.size - 1))
+                                     torch.from_numpy(np.repeat(1.0 / deg1, np.diff(rp1))), (rp1.size - 1, rp0.size - 1))
         return agg0, self0, torch.sparse.mm(a1, h)
 
     def step_csr(blk):
@@ -177,10 +244,10 @@ def run_cpu_arm(steps, warmup, budget_s=25.0, which=("coo", "csr")):
     for name, fn in (("coo", step_coo), ("csr", step_csr)):
         if name not in which:
             continue
-        for w in range(min(warmup, 2)):
+        for w in range(warmup):
             fn(blocks[w % len(blocks)])
         t0, n, nbytes = time.perf_counter(), 0, 0
-        while n < steps and (time.perf_counter() - t0) < budget_s / len(which):
+        while n < steps and (n == 0 or (time.perf_counter() - t0) < budget_s / len(which)):
             blk = blocks[n % len(blocks)]
             fn(blk)
             nbytes += cpu_step_bytes(blk)
@@ -188,7 +255,203 @@ def run_cpu_arm(steps, warmup, budget_s=25.0, which=("coo", "csr")):
         dt = time.perf_counter() - t0
         res[name] = {"gbs": nbytes / dt / 1e9, "ms_per_step": dt / max(n, 1) * 1e3, "steps": n}
     best = max(res, key=lambda k: res[k]["gbs"])
-    return {"value": res[best]["gbs"], "best": best, "variants": res, "cores": cores}
+    return {"value": res[best]["gbs"], "best": best, "variants": res, "cores": cores, "origin": origin,
+            "block0": {"n_dst": int(blocks[0][0].size - 1), "nnz": int(blocks[0][1].size)}}
+
+
+def reference_arm(args):
+    r = run_cpu_arm(max(args.steps, 1), args.warmup, budget_s=120.0, seed=args.seed)
+    v = r["variants"][r["best"]]
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": v["steps"], "warmup": args.warmup, "ms_per_step": v["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": bench_config(args.gpus, r["block0"]["n_dst"], r["block0"]["nnz"]),
+            "cpu_baseline": {"value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": "port",
+                             "sample": "%d steps over the %d mini-batches of the workload; inputs: %s; best of "
+                                       "torch.sparse.mm on a COO block rebuilt inside every step as the reference's forward "
+                                       "does (gcnconv.py:31, gcn_model.py:68-76) and the OpenMP CSR port (oracle.c): %s"
+                                       % (v["steps"], N_BATCHES, r["origin"],
+                                          json.dumps({k: round(x["gbs"], 2) for k, x in r["variants"].items()}))},
+            "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------- extras --
+def extra_epoch(args, rank, world, dev, row_ptr, col_idx, table, gen, barrier):
+    """Sampled GraphSAGE TRAINING epoch, Reddit-shaped: 2-layer SAGE 602 -> 256 -> 41, fanout 25/10, batch 1024/GPU,
+    Adam; every rank trains on its shard of the 153,756 train seeds (first 66 % of the nodes, use_ddp-style split),
+    gradients all-reduced as one flat buffer per step."""
+    import torch
+    import torch.distributed as dist
+    import dgll_b200.nn as dnn
+    from dgll_b200 import pipelined as PL, train as T
+    n_train = int(0.66 * N_NODES)
+    torch.manual_seed(args.seed)
+    labels = torch.randint(0, 41, (N_NODES,), device=dev, generator=gen)
+    model = dnn.GraphSAGE(FEAT, HIDDEN, 41, 2, torch.relu, 0.0).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
+    perm_e = torch.randperm(n_train, device=dev, generator=torch.Generator(device=dev).manual_seed(args.seed))
+    shard = perm_e[rank::world].contiguous()
+    res = {}
+    for prec in ("fp32", "bf16"):
+        out = {}
+        T.sage_epoch(model, opt, table, labels, FEAT, row_ptr, col_idx, shard[:8 * BATCH], FANOUTS, BATCH,
+                     rng_seed=1, precision=prec)                                  # warm-up: 8 batches
+        barrier()
+        r_e2e = T.sage_epoch(model, opt, table, labels, FEAT, row_ptr, col_idx, shard, FANOUTS, BATCH,
+                             rng_seed=2, precision=prec)                           # Python-dispatched, sampler in the loop
+        out["epoch_s_sampler_in_loop"] = r_e2e["time_s"]
+        out["loss"] = round(r_e2e["loss"], 4)
+        g_err = None
+        g_loop = g_loop2 = float("nan")
+        try:
+            # ONE graph launch per mini-batch: sampler, block builder, fused gather+aggregation, training step, flat
+            # all-reduce and Adam inside two ping-pong CUDA graphs (dgll_b200.pipelined)
+            opt_g = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=True)
+            tr = PL.PipelinedSageTrainer(model, opt_g, labels, row_ptr, col_idx, FEAT, table=table, batch_size=BATCH,
+                                         fanouts=FANOUTS, precision=prec, rng_seed=4, max_seeds=shard.numel())
+            tr.set_seeds(shard)
+            tr.capture()
+            tr.epoch(shard[:4 * BATCH])
+            barrier()
+            g_loop = tr.epoch(shard)["time_s"]
+            barrier()
+            g_loop2 = tr.epoch(shard)["time_s"]
+            for p in model.parameters():
+                p.grad = None
+            del tr, opt_g
+        except Exception as ex:
+            g_err = "%s: %s" % (type(ex).__name__, str(ex)[:200])
+        t = torch.tensor([out["epoch_s_sampler_in_loop"], g_loop, g_loop2], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["epoch_s_sampler_in_loop"] = round(t[0].item(), 4)
+        out["epoch_s_sampler_in_loop_cuda_graph"] = round(min(t[1].item(), t[2].item()), 5)
+        out["epoch_s_sampler_in_loop_cuda_graph_runs"] = [round(t[1].item(), 5), round(t[2].item(), 5)]
+        out["batches_per_gpu"] = r_e2e["n_batches"]
+        if g_err:
+            out["cuda_graph_error"] = g_err
+        res[prec] = out
+    return {"model": "GraphSAGE-mean 2-layer 602-256-41, fanout 25/10, batch 1024/GPU, Adam, fwd+bwd+step",
+            "train_seeds": n_train, "scaling": "strong (the 153,756 train seeds are split over the ranks)",
+            "cuda_graph": "one launch per mini-batch: device sampler + block builder + fused gather/aggregation || "
+                          "training step + flat all-reduce + Adam (dgll_b200.pipelined)",
+            "gemm": res}
+
+
+def extra_partitioned(args, rank, world, dev, barrier):
+    """BASELINE configs[4]: GraphSAGE on a papers100M-shaped graph, features node-range partitioned over the ranks."""
+    import torch
+    import torch.distributed as dist
+    import dgll_b200.nn as dnn
+    from dgll_b200 import graphs as G, parallel as P, pipelined as PL, train as T
+    N0, NNZ0, F, C = G.SHAPES["papers100m"]
+    scale = float(os.environ.get("BENCH_C5_SCALE", "1.0"))
+    N, NNZ = int(N0 * scale), int(NNZ0 * scale)
+    t0 = time.perf_counter()
+    row_ptr, col = G.rmat_csr_large(N, NNZ, seed=args.seed, device=dev)            # topology replicated on every rank
+    deg = row_ptr[1:] - row_ptr[:-1]
+    max_deg = int(deg.max().item())
+    del deg
+    lo, hi = P.local_range(rank, N, world)
+    table = G.feature_table(hi - lo, F, seed=100 + rank, device=dev)               # this rank's feature rows, fp32
+    labels = torch.randint(0, C, (hi - lo,), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+    n_train = int(1207179 * scale)
+    per_rank = max(n_train // world, 64 * BATCH)
+    seeds = lo + torch.randperm(hi - lo, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))[:per_rank]
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    out = {"graph": "R-MAT (0.57,0.19,0.19,0.05), N=%d nnz=%d max in-degree %d, topology replicated" % (N, NNZ, max_deg),
+           "features": "F=%d fp32, node-range partitioned: %d rows (%.1f GB) per GPU" % (F, hi - lo, (hi - lo) * F * 4 / 1e9),
+           "model": "GraphSAGE-mean 2-layer %d-256-%d, fanout 25/10, batch 1024 per GPU, Adam, tcgen05 bf16 transforms" % (F, C),
+           "train_seeds": n_train, "scaling": "weak per step (1,024 seeds per GPU); the epoch is the fixed 1,207,179 seeds",
+           "setup_s": round(setup_s, 1), "mechanisms": {}}
+
+    def run_peer(tbl, tag):
+        sharded = P.PeerShardedTable(N, tbl)
+        torch.manual_seed(args.seed)
+        model = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=True)
+        tr = PL.PipelinedSageTrainer(model, opt, labels, row_ptr, col, F, sharded=sharded, batch_size=BATCH,
+                                     fanouts=FANOUTS, precision="bf16", rng_seed=11, label_offset=lo, max_seeds=per_rank)
+        tr.set_seeds(seeds)
+        tr.capture()
+        tr.epoch(seeds[:16 * BATCH])
+        barrier()
+        r = tr.epoch(seeds)                                  # the whole epoch, measured (not extrapolated)
+        barrier()
+        halo = tr.halo_stats()
+        stage = tr.stage_times(seeds[:24 * BATCH], steps=24)
+        t = torch.tensor([r["time_s"], stage["produce_ms_eager"], stage["train_ms_eager"], halo["remote_edge_fraction"],
+                          float(halo["remote_bytes_per_step"])], device=dev, dtype=torch.float64)
+        mx = t.clone()
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t /= world
+        n_b = r["n_batches"]
+        res = {"halo": "peer: remote rows read over NVLink by the input-layer aggregation kernel itself "
+                       "(dgllb_spmm_csr_sharded), no collective, no staging",
+               "step": "one CUDA graph per mini-batch: {sample + build block + sharded aggregation of batch i+1} || "
+                       "{train batch i + flat all-reduce + Adam}; overlap on at every N",
+               "epoch_s": round(mx[0].item(), 4), "batches_per_gpu": n_b,
+               "ms_per_step": round(mx[0].item() * 1e3 / n_b, 4),
+               "seeds_per_s": round(world * per_rank / mx[0].item(), 1),
+               "stage_ms_unoverlapped": {"sample+halo+aggregate (branch B)": round(mx[1].item(), 4),
+                                         "fwd+bwd+all-reduce+Adam (branch A)": round(mx[2].item(), 4)},
+               "remote_edge_fraction_measured": round(t[3].item(), 4),
+               "nvlink_bytes_in_per_gpu_per_step": int(t[4].item()), "loss": round(r["loss"], 4)}
+        for p in model.parameters():
+            p.grad = None
+        barrier()                                            # no peer may still be reading this rank's shard
+        sharded.close()
+        out["mechanisms"][tag] = res
+
+    def run_nccl():
+        hx = P.HaloExchange(N, table)
+        torch.manual_seed(args.seed)
+        model = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=True)
+        tr = T.GraphedSageTrainer(model, opt, None, labels, BATCH, FANOUTS, n_feat=F, precision="bf16",
+                                  capture_collectives=True, label_offset=lo)
+        steps = 40
+
+        def produce(first, count):
+            for k in range(count):
+                s = seeds[(first + k) * BATCH:(first + k + 1) * BATCH]
+                blocks = G.sample_blocks(row_ptr, col, s, FANOUTS, rng_seed=rank * 100003 + first + k)
+                yield s, blocks, hx.fetch(blocks[0].src_ids)
+
+        first = next(produce(0, 1))
+        tr.load(*first)
+        tr.capture()
+        tr.epoch(produce(0, 5), overlap=False)
+        barrier()
+        hx.stats = {"rows": 0, "remote_rows": 0, "calls": 0}
+        r = tr.epoch(produce(5, steps), overlap=False)       # exchange and step on ONE stream: same communicator, ordered
+        t = torch.tensor([r["time_s"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t[0].item() * 1e3 / steps
+        out["mechanisms"]["nccl_all_to_all"] = {
+            "halo": "NCCL all_to_all_single: counts, ids, rows (parallel.HaloExchange, one host read-back per step), then "
+                    "the step graph with the flat all-reduce and Adam captured; exchange and step on one stream",
+            "steps": steps, "ms_per_step": round(ms, 4), "seeds_per_s": round(world * BATCH / (ms * 1e-3), 1),
+            "epoch_s_extrapolated": round(per_rank / BATCH * ms * 1e-3, 4),
+            "remote_row_fraction_measured": round(hx.stats["remote_rows"] / max(hx.stats["rows"], 1), 4),
+            "unique_src_rows_per_step": round(hx.stats["rows"] / max(hx.stats["calls"], 1), 1), "loss": round(r["loss"], 4)}
+        for p in model.parameters():
+            p.grad = None
+
+    for tag, fn in (("peer_fp32", lambda: run_peer(table, "peer_fp32")), ("nccl_all_to_all", run_nccl),
+                    ("peer_bf16_table", lambda: run_peer(table.to(torch.bfloat16), "peer_bf16_table"))):
+        try:
+            fn()
+        except Exception as ex:
+            out["mechanisms"][tag] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+        barrier()
+    return out
 
 
 # --------------------------------------------------------------------- GPU arm --
@@ -200,36 +463,21 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-epoch", action="store_true", help="skip the sampled-GraphSAGE training-epoch extra")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the papers100M-shaped partitioned extra")
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = ("GraphSAGE-mean 2-layer fanout 25/10 batch 1024, aggregation path of one mini-batch, synthetic "
-                "Reddit-shaped graph N=232965 nnz=114615892 F=602 fp32")
-    metric = "SpMM aggregation GB/s (algorithmic bytes, sampled GraphSAGE-mean blocks)"
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        r = run_cpu_arm(max(args.steps, 1), args.warmup, budget_s=60.0)
-        v = r["variants"][r["best"]]
-        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "GB/s", "n_gpus": args.gpus,
-                "steps": v["steps"], "warmup": min(args.warmup, 2), "ms_per_step": v["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": workload, "flush": "feature table 563 MB > L2"},
-                "cpu_baseline": {"value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": "port",
-                                 "sample": "%d mini-batches of the same block shapes; best of torch.sparse.mm COO "
-                                           "(reference-faithful, gcnconv.py:31) and OpenMP CSR port (oracle.c): %s"
-                                           % (v["steps"], json.dumps({k: round(x["gbs"], 2) for k, x in r["variants"].items()}))},
-                "e2e": {"value": r["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        if rank == 0:
+            reference_arm(args)
         return
 
     import torch
     import torch.distributed as dist
-    from dgll_b200 import _lib, graphs as G, kernels as K
+    from dgll_b200 import _lib, kernels as K
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -239,78 +487,75 @@ def main():
 
     # ---- synthetic inputs, resident in HBM -------------------------------------------------------------
     t_setup = time.perf_counter()
-    row_ptr, col_idx = G.rmat_csr(N_NODES, NNZ, seed=args.seed, device=dev)
-    LD = int(os.environ.get("BENCH_LD", "604"))
-    table = G.feature_table(N_NODES, FEAT, seed=args.seed, device=dev, pad_to=LD)  # [N, 604] fp32, 563 MB > L2
-    gen = torch.Generator(device=dev).manual_seed(args.seed + 1000 * rank)
-    n_train = int(0.66 * N_NODES)
-    perm = torch.randperm(n_train, device=dev, generator=gen)
-    batches = []
-    for b in range(N_BATCHES):
-        seeds = perm[b * BATCH:(b + 1) * BATCH]
-        blocks = G.sample_blocks(row_ptr, col_idx, seeds, FANOUTS, rng_seed=args.seed * 7919 + b + 131 * rank)
-        b0, b1 = blocks
-        batches.append({
-            "rp0": b0.row_ptr, "col0": b0.col_global, "dst0": b0.dst_ids.contiguous(), "n_dst0": b0.num_dst,
-            "rp1": b1.row_ptr, "col1": b1.col, "n_dst1": b1.num_dst,
-            "agg0": torch.empty((b0.num_dst, FEAT), device=dev), "self0": torch.empty((b0.num_dst, LD), device=dev),
-            "agg1": torch.empty((b1.num_dst, HIDDEN), device=dev),
-            "h1": torch.randn((b0.num_dst, HIDDEN), device=dev, generator=gen),
-        })
+    row_ptr, col_idx, table, gen, batches = make_inputs(args.seed, rank, dev)
     for bt in batches:
+        bt["agg0"] = torch.empty((bt["n_dst0"], LD32), device=dev)[:, :FEAT]      # 16-byte rows: 128-bit stores
+        bt["self0"] = torch.empty((bt["n_dst0"], LD32), device=dev)
+        bt["agg1"] = torch.empty((bt["n_dst1"], HIDDEN), device=dev)
+        bt["h1"] = torch.randn((bt["n_dst0"], HIDDEN), device=dev, generator=gen)
         bt["bytes0"] = alg_bytes_spmm(bt["col0"].numel(), bt["n_dst0"], FEAT, rp=4)
-        bt["bytes"] = (bt["bytes0"] + alg_bytes_gather(bt["n_dst0"], 604 * 4)
-                       + alg_bytes_spmm(bt["col1"].numel(), bt["n_dst1"], HIDDEN, rp=4))
+        bt["bytes_rest"] = (alg_bytes_gather(bt["n_dst0"], LD32 * 4)
+                            + alg_bytes_spmm(bt["col1"].numel(), bt["n_dst1"], HIDDEN, rp=4))
+        bt["bytes"] = bt["bytes0"] + bt["bytes_rest"]
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
 
-    view = table[:, :FEAT]
+    def make_step(tbl):
+        view = tbl[:, :FEAT]
 
-    def step(bt, ev=None):
-        if ev is not None:
-            ev[0].record()
-        K.spmm_csr(bt["rp0"], bt["col0"], view, reduce="mean", out=bt["agg0"])
-        if ev is not None:
-            ev[1].record()
-        K.gather_rows(table, bt["dst0"], out=bt["self0"])
-        K.spmm_csr(bt["rp1"], bt["col1"], bt["h1"], reduce="mean", out=bt["agg1"])
+        def step(bt, ev=None):
+            if ev is not None:
+                ev[0].record()
+            K.spmm_csr(bt["rp0"], bt["col0"], view, reduce="mean", out=bt["agg0"])
+            if ev is not None:
+                ev[1].record()
+            K.gather_rows(table, bt["dst0"], out=bt["self0"])
+            K.spmm_csr(bt["rp1"], bt["col1"], bt["h1"], reduce="mean", out=bt["agg1"])
+        return step
+
+    step = make_step(table)
+    view = table[:, :FEAT]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_loop(step_fn, steps, warmup, profile=False):
+        """W warm-up steps, then exactly ``steps`` steps between two events; the dominant kernel is bracketed by its own
+        event pair on every 4th step (events cost ~1-2 us of stream time each)."""
+        for w in range(warmup):
+            step_fn(batches[w % N_BATCHES])
+        barrier()
+        KEV = 4
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range((steps + KEV - 1) // KEV)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if profile:
+            torch.cuda.profiler.start()
+        e0.record()
+        for s in range(steps):
+            step_fn(batches[s % N_BATCHES], kev[s // KEV] if s % KEV == 0 else None)
+        e1.record()
+        barrier()
+        if profile:
+            torch.cuda.profiler.stop()
+        return e0.elapsed_time(e1), sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+
     # ---- device-resident timing ------------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
     for w in range(args.warmup):
         step(batches[w % N_BATCHES])
     barrier()
-    clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     l0 = _lib.launch_count()
-    # the dominant kernel is bracketed by its own event pair on every 4th step (events cost ~1-2 us of stream time each)
-    KEV = 4
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range((args.steps + KEV - 1) // KEV)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     prof = os.environ.get("BENCH_PROFILE") == "1"   # ncu --profile-from-start off: capture the timed steps only
-    if prof:
-        torch.cuda.profiler.start()
-    e0.record()
-    total_bytes = 0
-    for s in range(args.steps):
-        bt = batches[s % N_BATCHES]
-        step(bt, kev[s // KEV] if s % KEV == 0 else None)
-        total_bytes += bt["bytes"]
-    e1.record()
-    barrier()
-    if prof:
-        torch.cuda.profiler.stop()
+    ms, k_ms = timed_loop(step, args.steps, 0, profile=prof)
     launches = _lib.launch_count() - l0
-    ms = e0.elapsed_time(e1)
-    k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
-    k_bytes = sum(batches[s % N_BATCHES]["bytes0"] for s in range(0, args.steps, KEV)) / len(kev)
+    total_bytes = sum(batches[s % N_BATCHES]["bytes"] for s in range(args.steps))
+    k_bytes = sum(batches[s % N_BATCHES]["bytes0"] for s in range(0, args.steps, 4)) / len(range(0, args.steps, 4))
 
     # ---- end to end: blocks in pinned host memory -> H2D -> kernels -> D2H of the layer-1 aggregate -----
     # Each mini-batch's block arrays (row_ptr0, col0, dst ids, row_ptr1, col1; all int32) live in ONE pinned host
@@ -435,58 +680,78 @@ def main():
         torch.cuda.synchronize()
         assert torch.equal(out_host[(args.steps - 1) % 2][:batches[last]["n_dst1"]].to(dev), ref_out), "e2e graph result"
     clk = clocks.stop() if rank == 0 else None
+    del graphs
 
-    # ---- extra: sampled GraphSAGE TRAINING epoch (second half of BASELINE.json's metric) ------------------------
-    # 2-layer SAGE 602 -> 256 -> 41, fanout 25/10, batch 1024/GPU, Adam; every rank trains on its shard of the
-    # 153,756 train seeds (first 66 % of the nodes), gradients all-reduced as one flat buffer per step.
+    # ---- same-box GPU comparator: the library SpMM behind the reference's layers -------------------------------
+    gpu_baseline = None
+    if rank == 0:
+        try:
+            mats = []
+            for bt in batches:
+                deg = (bt["rp0"][1:] - bt["rp0"][:-1]).to(torch.float32).clamp(min=1)
+                vals = torch.repeat_interleave(1.0 / deg, (bt["rp0"][1:] - bt["rp0"][:-1]).long())
+                mats.append(torch.sparse_csr_tensor(bt["rp0"].long(), bt["col0"].long(), vals, size=(bt["n_dst0"], N_NODES)))
+            xc = view.contiguous()                                   # torch.sparse.mm needs a dense contiguous operand
+            for m in mats[:3]:
+                torch.sparse.mm(m, xc)
+            torch.cuda.synchronize()
+            evs = []
+            for s in range(min(args.steps, 64)):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                torch.sparse.mm(mats[s % N_BATCHES], xc)
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            t_lib = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+            chk = (torch.sparse.mm(mats[0], xc) - batches[0]["agg0"]).abs().max().item()
+            gpu_baseline = {"kernel": "torch.sparse.mm(CSR on CUDA = cuSPARSE, the call behind gcnconv.py:31 / gcn_model.py:76), "
+                                      "layer-0 aggregation of the same mini-batches", "kernel_ms": t_lib,
+                            "value": k_bytes / (t_lib * 1e-3) / 1e9, "unit": "GB/s", "ours_kernel_ms": k_ms,
+                            "speedup": t_lib / k_ms, "max_abs_diff_vs_ours": chk}
+            del mats, xc
+        except Exception as ex:
+            gpu_baseline = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+
+    # ---- extra: the same step with the feature table stored in bf16 ----------------------------------------------
+    bf16 = None
+    try:
+        t16 = torch.zeros((N_NODES, LD16), dtype=torch.bfloat16, device=dev)
+        t16[:, :FEAT] = view.to(torch.bfloat16)
+        step16 = make_step(t16)
+        ms16, k16 = timed_loop(step16, args.steps, max(args.warmup, 3))
+        b16 = sum(alg_bytes_spmm(batches[s % N_BATCHES]["col0"].numel(), batches[s % N_BATCHES]["n_dst0"], FEAT, b=2, rp=4)
+                  + batches[s % N_BATCHES]["bytes_rest"] for s in range(args.steps))
+        kb16 = sum(alg_bytes_spmm(batches[s % N_BATCHES]["col0"].numel(), batches[s % N_BATCHES]["n_dst0"], FEAT, b=2, rp=4)
+                   for s in range(0, args.steps, 4)) / len(range(0, args.steps, 4))
+        ref16 = K.spmm_csr(batches[0]["rp0"], batches[0]["col0"], view, reduce="mean")
+        got16 = K.spmm_csr(batches[0]["rp0"], batches[0]["col0"], t16[:, :FEAT], reduce="mean")
+        bf16 = {"table": "bf16, row stride 608 (283 MB)", "ms_per_step": ms16 / args.steps,
+                "value_alg_GBps_at_2_bytes": b16 / (ms16 * 1e-3) / 1e9, "kernel_ms": k16,
+                "kernel_alg_GBps": kb16 / (k16 * 1e-3) / 1e9, "speedup_vs_fp32_step": (ms / args.steps) / (ms16 / args.steps),
+                "max_rel_err_vs_fp32_table": ((got16 - ref16).abs().max() / ref16.abs().max()).item(),
+                "scope": "per GPU (rank 0)"}
+        del t16, ref16, got16
+    except Exception as ex:
+        bf16 = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+
+    # ---- extras: training epoch (Reddit-shaped) and the partitioned papers100M-shaped run -------------------------
     epoch = None
     if not args.no_epoch:
-        import dgll_b200.nn as dnn
-        from dgll_b200 import train as T
-        torch.manual_seed(args.seed)
-        labels = torch.randint(0, 41, (N_NODES,), device=dev, generator=gen)
-        model = dnn.GraphSAGE(FEAT, HIDDEN, 41, 2, torch.relu, 0.0).to(dev)
-        opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True)
-        perm_e = torch.randperm(n_train, device=dev, generator=torch.Generator(device=dev).manual_seed(args.seed))
-        shard = perm_e[rank::world].contiguous()              # use_ddp-style split of the shuffled train seeds
-        res = {}
-        for prec in ("fp32", "bf16"):
-            T.sage_epoch(model, opt, table, labels, FEAT, row_ptr, col_idx, shard[:8 * BATCH], FANOUTS, BATCH,
-                         rng_seed=1, precision=prec)                                  # warm-up: 8 batches
-            barrier()
-            r_e2e = T.sage_epoch(model, opt, table, labels, FEAT, row_ptr, col_idx, shard, FANOUTS, BATCH,
-                                 rng_seed=2, precision=prec)                           # sampler in the loop
-            pre = T.make_batches(row_ptr, col_idx, shard, FANOUTS, BATCH, rng_seed=3)
-            barrier()
-            r_pre = T.sage_epoch(model, opt, table, labels, FEAT, batches=pre, precision=prec)
-            # the same step captured once as a CUDA graph on fixed-capacity block buffers (train.GraphedSageTrainer):
-            # (a) pre-sampled blocks, (b) device sampler + block builder run eagerly, training step replayed
-            g_pre = g_loop = float("nan")
-            g_err = None
-            try:
-                opt_g = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=True)
-                tr = T.GraphedSageTrainer(model, opt_g, table, labels, BATCH, FANOUTS, precision=prec)
-                tr.load(*pre[0])
-                tr.capture()
-                barrier()
-                g_pre = tr.epoch(pre)["time_s"]
-                barrier()
-                g_loop = tr.epoch(T.iter_batches(row_ptr, col_idx, shard, FANOUTS, BATCH, rng_seed=4))["time_s"]
-                del tr, opt_g
-            except Exception as ex:                                  # report, keep the eager numbers
-                g_err = "%s: %s" % (type(ex).__name__, str(ex)[:200])
-            del pre
-            t = torch.tensor([r_e2e["time_s"], r_pre["time_s"], g_pre, g_loop], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            res[prec] = {"epoch_s_sampler_in_loop": round(t[0].item(), 4), "epoch_s_presampled": round(t[1].item(), 4),
-                         "epoch_s_presampled_cuda_graph": round(t[2].item(), 4),
-                         "epoch_s_sampler_in_loop_cuda_graph": round(t[3].item(), 4),
-                         "batches_per_gpu": r_e2e["n_batches"], "loss": round(r_e2e["loss"], 4)}
-            if g_err:
-                res[prec]["cuda_graph_error"] = g_err
-        epoch = {"model": "GraphSAGE-mean 2-layer 602-256-41, fanout 25/10, batch 1024/GPU, Adam, fwd+bwd+step",
-                 "train_seeds": int(perm.numel()), "gemm": res}
+        try:
+            epoch = extra_epoch(args, rank, world, dev, row_ptr, col_idx, table, gen, barrier)
+        except Exception as ex:
+            epoch = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+    n_dst0, nnz0 = batches[0]["n_dst0"], batches[0]["col0"].numel()
+    del row_ptr, col_idx, table, view, batches, host, dev_buf, step
+    torch.cuda.empty_cache()
+    partitioned = None
+    if not args.no_partitioned:
+        try:
+            partitioned = extra_partitioned(args, rank, world, dev, barrier)
+        except Exception as ex:
+            partitioned = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+        torch.cuda.empty_cache()
 
     # ---- max over ranks ----------------------------------------------------------------------------------
     stats = torch.tensor([ms, e2e_ms, float(total_bytes), float(e2e_bytes), float(launches)], device=dev,
@@ -506,30 +771,30 @@ def main():
     peak, peak_src = peaks()
     value = total_bytes / (ms * 1e-3) / 1e9
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
     line = {
-        "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "batch": BATCH, "fanouts": list(FANOUTS), "hidden": HIDDEN,
-                   "parallelism": "dp%d (batch axis; graph+features replicated)" % world,
-                   "flush": "inputs larger than L2: 563 MB feature table, %d distinct mini-batches cycled" % N_BATCHES,
-                   "block0": {"n_dst": batches[0]["n_dst0"], "nnz": batches[0]["col0"].numel()},
-                   "setup_s": round(setup_s, 1)},
-        "roofline": {"bound": "hbm", "kernel": "spmm_rowslab_kernel<float,4,32> (layer-0 mean aggregation, F=602)",
+        "config": bench_config(world, n_dst0, nnz0),
+        "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel<float,5,4> (layer-0 mean aggregation, F=602, whole row per warp)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(), "traffic_source": "profiles/r01_spmm_headline.txt (ncu --set full)",
-                     "peak_source": peak_src, "kernel_ms": k_ms,
-                     "algorithmic_bytes_per_launch": k_bytes},
+                     "traffic": traffic, "traffic_source": "%s (ncu --set full)" % traffic_src if traffic_src else None,
+                     "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                     "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
+                     "note": "frac counts every edge's full source row (SURVEY §8 d); dram_frac counts the bytes DRAM "
+                             "actually moved — repeated source rows of a mini-batch are served by L2"},
         "e2e": {"value": e2e_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode},
-        "gpu_launches": launches, "clocks": clk, "epoch": epoch,
+        "gpu_launches": launches, "clocks": clk, "gpu_baseline": gpu_baseline, "bf16_table": bf16,
+        "epoch": epoch, "partitioned": partitioned, "setup_s": round(setup_s, 1),
     }
     if not args.no_cpu_baseline and world == 1:
-        r = run_cpu_arm(6, 1, budget_s=24.0)
+        r = run_cpu_arm(8, 1, budget_s=24.0, seed=args.seed, n_blocks=4)
         line["cpu_baseline"] = {
             "value": r["value"], "unit": "GB/s", "cores": r["cores"], "kind": "port",
-            "sample": "<=6 mini-batches of the same block shapes per variant, ~12 s each; best=%s; %s" % (
-                r["best"], json.dumps({k: round(x["gbs"], 2) for k, x in r["variants"].items()}))}
+            "sample": "<=8 steps per variant (~12 s each) on 4 of the GPU arm's own mini-batches (%s); best=%s; %s" % (
+                r["origin"], r["best"], json.dumps({k: round(x["gbs"], 2) for k, x in r["variants"].items()}))}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -27,10 +27,13 @@ SIGNATURES = {
     "dgllb_last_error": (c_char_p, []),
     "dgllb_device_info": (_I, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
     "dgllb_launch_count": (_L, []),
+    "dgllb_set_option": (_I, [c_char_p, c_char_p]),
+    "dgllb_get_option": (_I, [c_char_p, POINTER(c_int)]),
     "dgllb_csr_plan_create": (_I, [_P, _I, _L, _I, _P, POINTER(c_void_p)]),
     "dgllb_csr_plan_info": (_I, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
     "dgllb_csr_plan_destroy": (None, [_P]),
     "dgllb_spmm_csr": (_I, [_P, _I, _P, _P, _P, _I, _L, _P, _L, _L, _L, _L, _I, _I, _P, _P, _L, _P, _I, _P, _P, _P]),
+    "dgllb_spmm_csr_sharded": (_I, [_P, _I, _P, _P, _P, _I, _L, _L, _I, _P, _L, _L, _I, _I, _P]),
     "dgllb_sddmm_csr": (_I, [_P, _I, _P, _P, _L, _P, _L, _P, _L, _I, _P]),
     "dgllb_spmm_max_backward": (_I, [_P, _P, _P, _L, _P, _L, _L, _I, _P]),
     "dgllb_csr_transpose": (_I, [_P, _I, _P, _P, _L, _L, _L, _P, _P, _P, _P, _P]),
@@ -101,3 +104,15 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib().dgllb_launch_count())
+
+
+def set_option(name, value):
+    """Tuning option of the library (see ``dgllb_set_option`` in include/dgll_b200.h); ``None`` = default."""
+    v = None if value is None else str(value).encode()
+    check(lib().dgllb_set_option(name.encode(), v), "set_option")
+
+
+def get_option(name):
+    out = c_int()
+    check(lib().dgllb_get_option(name.encode(), ctypes.byref(out)), "get_option")
+    return out.value

@@ -251,11 +251,8 @@ extern "C" int dgllb_bin_spmm_csr(const void* row_ptr, int row_ptr_is64, const i
             plan->heavy_rows, plan->n_heavy_rows, static_cast<uint32_t*>(out), ldo, F);
         DGLLB_LAUNCH_CHECK();
     }
-    int tb = 64;  // small blocks retire evenly on ragged rows (4.54 -> 4.26 ms, Reddit-shaped)
-    if (const char* e = getenv("DGLLB_BIN_TB")) {
-        const int v = atoi(e);
-        if (v == 32 || v == 64 || v == 128 || v == 256) tb = v;
-    }
+    int tb = opt_get(OPT_BIN_TB);  // default 64: small blocks retire evenly on ragged rows (4.54 -> 4.26 ms, Reddit-shaped)
+    if (!(tb == 32 || tb == 64 || tb == 128 || tb == 256)) tb = 64;
     const long long blocks = (n_dst * 32 + tb - 1) / tb;
     const long long hblocks = heavy ? (plan->n_items * 32 + tb - 1) / tb : 0;
     DGLLB_REQUIRE(blocks < (1ll << 31) && hblocks < (1ll << 31), "bin_spmm: grid too large");

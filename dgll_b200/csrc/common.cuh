@@ -25,6 +25,21 @@ struct DevInfo {
 // Cached properties of the current device (thread-safe, per device index).
 int get_devinfo(DevInfo* out);
 
+// Tuning options: integers initialised ONCE from the environment (DGLLB_<NAME>) and changed afterwards only through
+// dgllb_set_option — no getenv() on any launch path.  0 always means "library default".
+enum Opt {
+    OPT_SPMM_KERNEL = 0,   // 0 auto, 1 rowsplit, 2 stream, 3 wholerow
+    OPT_SPMM_TB,           // rowsplit kernel block size
+    OPT_ROWS_TB, OPT_ROWS_NS, OPT_ROWS_D,   // whole-row kernel: block size, slabs per warp, window depth
+    OPT_GAT_KERNEL,        // 0 auto, 1 generic (lane-group), 2 whole-row
+    OPT_GAT_ROW_WARPS, OPT_GAT_BWD_TB,
+    OPT_BIN_TB,
+    OPT_GEMM_KERNEL,       // 0 auto; see gemm_tcgen05.cu
+    OPT_NVTX,              // 1 = emit NVTX ranges around the entry points that mirror the reference's ranges
+    OPT_COUNT
+};
+int opt_get(Opt o);
+
 #define DGLLB_CUDA_TRY(expr)                                                        \
     do {                                                                            \
         cudaError_t _e = (expr);                                                    \

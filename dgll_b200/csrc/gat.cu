@@ -720,8 +720,7 @@ __global__ void gat_bwd_combine_node_kernel(const GatBwdParams p) {
 }
 
 static int gat_bwd_block_threads() {
-    int tb = 64;  // small blocks retire evenly on ragged rows: 64.0 -> 55.9 ms (products-shaped)
-    if (const char* e = getenv("DGLLB_GAT_BWD_TB")) tb = atoi(e);
+    const int tb = opt_get(OPT_GAT_BWD_TB);  // default 64: small blocks retire evenly on ragged rows, 64.0 -> 55.9 ms (products-shaped)
     return (tb == 32 || tb == 64 || tb == 128 || tb == 256) ? tb : 64;
 }
 
@@ -821,9 +820,9 @@ static int launch_gat_fwd(GatParams& p, const dgllb_csr_plan* plan, cudaStream_t
     // degree-50 graph it runs at the SpMM rate (20.5 ms vs 19.2 ms, products-sized); on skewed graphs it needs the
     // nnz-split plan for long rows (a 89K-edge row would otherwise be one warp's job).  DGLLB_GAT_KERNEL=group|row pins.
     const int FD = p.heads * p.D;
-    const char* force = getenv("DGLLB_GAT_KERNEL");
+    const int force = opt_get(OPT_GAT_KERNEL);   // 1 = generic lane-group kernel, 2 = whole-row kernel
     const bool row_ok = VE == 4 && p.heads <= 4 && FD >= 32 && FD <= 512;  // below 32 floats most lanes of a warp would idle
-    if (row_ok && !(force && force[0] == 'g')) {
+    if (row_ok && force != 1) {
         const bool heavy = plan && plan->n_heavy_rows > 0;
         float* ws = nullptr;
         p.chunk = heavy ? plan->chunk_edges : 0;
@@ -838,8 +837,8 @@ static int launch_gat_fwd(GatParams& p, const dgllb_csr_plan* plan, cudaStream_t
         p.ws = ws;
         // one warp per block: with 8 warps a block kept its registers until its longest row was done (achieved
         // occupancy 27 %, profiles/r01_gat_fwd_bwd.txt); 4 edges in flight per warp (8 spills)
-        int cw = 1;  // DGLLB_GAT_ROW_WARPS=1|4|8 pins the block size (measurement aid)
-        if (const char* cfg = getenv("DGLLB_GAT_ROW_WARPS")) cw = atoi(cfg);
+        int cw = opt_get(OPT_GAT_ROW_WARPS);  // option gat_row_warps=1|4|8 pins the block size (measurement aid)
+        if (cw <= 0) cw = 1;
         const long long blocks = (p.n_dst + cw - 1) / cw;
         const long long hblocks = (p.n_items + cw - 1) / cw;
         DGLLB_REQUIRE(blocks < (1ll << 31) && hblocks < (1ll << 31), "gat_forward: grid too large");

@@ -46,8 +46,8 @@ struct SpmmParams {
 // run the aggregation kernel(s) for a filled parameter block (spmm.cu)
 int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan, cudaStream_t st);
 
-// TMA-staged aggregation (spmm_bulk.cu); DGLLB_ERR_UNSUPPORTED = shape not taken, caller falls through
-int spmm_bulk_try(const SpmmParams& p, int x_dtype, long long nnz, cudaStream_t st);
+// whole-row rolling-window aggregation for short rows (spmm_rows.cu); DGLLB_ERR_UNSUPPORTED = shape not taken
+int spmm_rows_try(const SpmmParams& p, int x_dtype, cudaStream_t st);
 
 // exact-fp32 SIMT GEMM (gemm_simt.cu)
 int gemm_simt(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,

@@ -25,9 +25,13 @@ gather_sharded_kernel(const char* const* __restrict__ shard_ptrs, long long rows
     for (long long row = warp0; row < n_rows; row += n_warps) {
         const long long id = ids64 ? reinterpret_cast<const long long*>(ids)[row]
                                    : static_cast<long long>(reinterpret_cast<const int*>(ids)[row]);
+        char* __restrict__ d = out + row * out_stride;
+        if (id < 0) {   // padding slot of a fixed-capacity id array: no remote read, the row reads as zeros
+            for (long long i = lane; i < row_bytes; i += 32) d[i] = 0;
+            continue;
+        }
         const long long shard = id / rows_per_shard;
         const char* __restrict__ s = shard_ptrs[shard] + (id - shard * rows_per_shard) * stride;
-        char* __restrict__ d = out + row * out_stride;
         if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(row_bytes)) & 15) == 0) {
             // up to 4 x 16 B per lane in flight (rows up to 2 KB move in one round)
             for (long long i = lane; i < n16; i += 128) {

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace dgllb {
 
@@ -55,11 +56,85 @@ int get_devinfo(DevInfo* out) {
     return DGLLB_OK;
 }
 
+// ---------------------------------------------------------------- options --
+struct OptDesc { const char* name; const char* env; const char* const* words; };
+static const char* const kSpmmWords[] = {"auto", "rowsplit", "stream", "wholerow", nullptr};
+static const char* const kGatWords[] = {"auto", "group", "row", nullptr};
+static const OptDesc kOpts[OPT_COUNT] = {
+    {"spmm_kernel", "DGLLB_SPMM_KERNEL", kSpmmWords},
+    {"spmm_tb", "DGLLB_SPMM_TB", nullptr},
+    {"rows_tb", "DGLLB_ROWS_TB", nullptr},
+    {"rows_ns", "DGLLB_ROWS_NS", nullptr},
+    {"rows_d", "DGLLB_ROWS_D", nullptr},
+    {"gat_kernel", "DGLLB_GAT_KERNEL", kGatWords},
+    {"gat_row_warps", "DGLLB_GAT_ROW_WARPS", nullptr},
+    {"gat_bwd_tb", "DGLLB_GAT_BWD_TB", nullptr},
+    {"bin_tb", "DGLLB_BIN_TB", nullptr},
+    {"gemm_kernel", "DGLLB_GEMM_KERNEL", nullptr},
+    {"nvtx", "DGLLB_NVTX", nullptr},
+};
+static std::atomic<int> g_opt[OPT_COUNT];
+static std::once_flag g_opt_once;
+
+static bool opt_parse(const OptDesc& d, const char* v, int* out) {
+    if (!v || !*v) { *out = 0; return true; }
+    if (d.words)
+        for (int k = 0; d.words[k]; ++k)
+            if (strcmp(d.words[k], v) == 0) { *out = k; return true; }
+    char* end = nullptr;
+    const long x = strtol(v, &end, 10);
+    if (end == v || *end) return false;
+    *out = static_cast<int>(x);
+    return true;
+}
+
+static void opt_init() {
+    for (int k = 0; k < OPT_COUNT; ++k) {
+        int v = 0;
+        if (const char* e = getenv(kOpts[k].env)) opt_parse(kOpts[k], e, &v);
+        g_opt[k].store(v, std::memory_order_relaxed);
+    }
+}
+
+int opt_get(Opt o) {
+    std::call_once(g_opt_once, opt_init);
+    return g_opt[o].load(std::memory_order_relaxed);
+}
+
 }  // namespace dgllb
 
 extern "C" {
 
-int dgllb_version(void) { return 1000; }
+int dgllb_version(void) { return 2000; }
+
+int dgllb_set_option(const char* name, const char* value) {
+    using namespace dgllb;
+    DGLLB_REQUIRE(name, "set_option: null name");
+    std::call_once(g_opt_once, opt_init);
+    for (int k = 0; k < OPT_COUNT; ++k) {
+        if (strcmp(kOpts[k].name, name) == 0) {
+            int v = 0;
+            DGLLB_REQUIRE(opt_parse(kOpts[k], value, &v), "set_option: bad value '%s' for %s", value, name);
+            g_opt[k].store(v, std::memory_order_relaxed);
+            return DGLLB_OK;
+        }
+    }
+    set_error("set_option: unknown option '%s'", name);
+    return DGLLB_ERR_INVALID;
+}
+
+int dgllb_get_option(const char* name, int* value_out) {
+    using namespace dgllb;
+    DGLLB_REQUIRE(name && value_out, "get_option: null pointer");
+    for (int k = 0; k < OPT_COUNT; ++k) {
+        if (strcmp(kOpts[k].name, name) == 0) {
+            *value_out = opt_get(static_cast<Opt>(k));
+            return DGLLB_OK;
+        }
+    }
+    set_error("get_option: unknown option '%s'", name);
+    return DGLLB_ERR_INVALID;
+}
 
 const char* dgllb_last_error(void) { return dgllb::t_err; }
 

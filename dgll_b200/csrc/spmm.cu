@@ -21,7 +21,6 @@
 // Algorithmic bytes per launch: nnz*(4 + [4 values] + F*b) + n_dst*(F*4 + r).
 #include "common.cuh"
 #include "internal.cuh"
-#include <stdlib.h>
 
 namespace dgllb {
 
@@ -566,11 +565,8 @@ static int launch_spmm(const SpmmParams& p, bool is_max, cudaStream_t st) {
     if (groups == 0) return DGLLB_OK;
     // 64-thread blocks: a block's registers are held until its slowest row finishes, so small blocks retire evenly on
     // ragged rows (headline block 0.127 -> 0.115 ms per step, full graphs 8 % faster at F=256; profiles/r01_block_size.md)
-    int tb = 64;
-    if (const char* e = getenv("DGLLB_SPMM_TB")) {
-        const int v = atoi(e);
-        if (v == 32 || v == 64 || v == 128 || v == 256) tb = v;
-    }
+    const int tb_env = opt_get(OPT_SPMM_TB);
+    const int tb = (tb_env == 32 || tb_env == 64 || tb_env == 128 || tb_env == 256) ? tb_env : 64;
     const int gpb = tb / LANES;
     const long long blocks = (groups + gpb - 1) / gpb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "spmm: grid too large (%lld blocks)", blocks);
@@ -642,20 +638,18 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
     p.out_vec = aligned16(p.out) && (p.ldo % 4 == 0);
     // streaming kernel: sum/mean over an explicit col_idx with a host-known nnz bound, wide rows, no split plan
     bool stream_ok = !is_max && !use_plan && p.col && !p.row_cnt && p.nnz_hint >= 0;
-    // Kernel choice (measured on B200, profiles/r01_kernels*.jsonl): one-warp-per-row wins on small sampled
-    // blocks, the rolling-LDG streaming kernel on large ones (>= 2^19 edges), row-split + nnz-split plan on
-    // skewed full graphs; the TMA-staged kernel is correct but slower than both LDG kernels on this part and
-    // only runs when pinned.  DGLLB_SPMM_KERNEL=rowsplit|stream|bulk pins one family (profiling / A-B runs).
-    const char* force = getenv("DGLLB_SPMM_KERNEL");
-    if (force && force[0] == 'r') stream_ok = false;
-    if (!force && p.nnz_hint < (1ll << 19)) stream_ok = false;
-    if (stream_ok && force && force[0] == 'b') {
-        rc = spmm_bulk_try(p, x_dtype, p.nnz_hint, st);
-        if (rc != DGLLB_ERR_UNSUPPORTED) {
-            if (rc != DGLLB_OK) return rc;
-            goto finalize;
-        }
+    // Kernel choice (measured on B200, profiles/r01_kernels*.jsonl, profiles/r02_spmm_rows_sweep.md): the whole-row
+    // rolling-window kernel (spmm_rows.cu) on sampled blocks, the row-aligned streaming kernel on large inputs
+    // (>= 2^19 edges), row-split + nnz-split plan on skewed full graphs.  Option spmm_kernel (env DGLLB_SPMM_KERNEL,
+    // dgllb_set_option) = rowsplit|stream|wholerow pins one family for A/B runs.
+    const int force = opt_get(OPT_SPMM_KERNEL);
+    const bool rows_ok = !is_max && !use_plan && (force == 0 ? (p.nnz_hint >= 0 && p.nnz_hint < (1ll << 19)) : force == 3);
+    if (rows_ok) {
+        rc = spmm_rows_try(p, x_dtype, st);
+        if (rc != DGLLB_ERR_UNSUPPORTED) return rc;
     }
+    if (force != 0 && force != 2) stream_ok = false;
+    if (force == 0 && p.nnz_hint < (1ll << 19)) stream_ok = false;
     if (x_dtype == DGLLB_F32) {
         // 128-bit LOADS need only the source table aligned; the output falls back to scalar stores by itself
         const bool vec = aligned16(p.X) && (p.ldx % 4 == 0);
@@ -668,7 +662,6 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
                       : launch_spmm_lanes<__nv_bfloat16, 1>(p, is_max, st);
     }
     if (rc != DGLLB_OK) return rc;
-finalize:
     if (use_plan && (p.addend || p.bias || p.epi)) {
         spmm_finalize_heavy_kernel<<<static_cast<unsigned>(plan->n_heavy_rows), 128, 0, st>>>(
             plan->heavy_rows, plan->n_heavy_rows, p.out, p.ldo, p.F, p.addend, p.ld_add, p.bias, p.epi);

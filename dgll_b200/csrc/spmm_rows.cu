@@ -1,0 +1,298 @@
+// spmm_rows.cu — whole-row neighbourhood aggregation for short rows (sampled blocks) on sm_100a, optionally
+// reading the source table IN PLACE from the shards of a node-range-partitioned table mapped over NVLink.
+//
+// Replaces, for sum/mean over rows of bounded degree: torch.spmm (dgll/nn/Convolution/gcnconv.py:31), the mean of
+// NeighborAggregator (sageconv.py:32-38), DGL's update_all(copy_u, mean) behind SAGEConv on a sampled block
+// (GPU Accelerator/CommGNNModel.py:72-77) together with the block's feature gather that feeds it
+// (dgll/data/dgraph.py:105, FeatureCache/storage.py:185-209) — the gather is the aggregation's own load.
+//
+// Why a second kernel next to spmm_rowslab_kernel (spmm.cu): ncu on the headline block (25-edge rows, F=602;
+// profiles/r01_spmm_headline.txt) showed the (row, 512-byte slab)-per-warp kernel issue-bound — ~50 warp
+// instructions per 512-byte load (per-slab index shuffles, 64-bit c*ldx multiplies, runtime null checks in the
+// unrolled loop), 67 % issue-active, 4 dependent rounds of 8 loads per row.  Here:
+//   * one warp owns a whole destination row: NS slabs (NS*512 bytes of every source row) per edge, so the column
+//     index shuffle and the address arithmetic are paid once per edge, not once per slab;
+//   * the lane that loaded col[e] computes the source row's BYTE ADDRESS once (shard lookup or base + c*stride);
+//     the address is broadcast with two shuffles, the slab offsets are LDG immediates;
+//   * a ROLLING window of D edges (D*NS 128-bit loads per lane) stays in flight across the whole row — no
+//     per-round drain;
+//   * everything optional (edge values, shards) is a template parameter: the inner loop has no runtime branch
+//     besides the row-length test.
+// Sharded mode is the B200-native halo exchange fused into the aggregation: shard = id / rows_per_shard
+// (node-range partition, SURVEY.md §8 e), remote rows are pulled by the kernel's own LDG.128 over NVSwitch.
+// Algorithmic bytes per launch: nnz*(4 + [4] + F*b) + n_dst*(F*4 + r).
+#include "common.cuh"
+#include "internal.cuh"
+
+namespace dgllb {
+
+struct RowsParams {
+    const void* row_ptr;
+    int rp64;
+    const int* col;
+    const float* vals;
+    const char* X;                     // single table (shard_ptrs == nullptr)
+    long long stride_bytes;            // source row stride in bytes
+    const char* const* shard_ptrs;     // device array of shard base pointers (sharded mode)
+    int rows_per_shard;
+    float* out;
+    long long ldo;
+    long long n_dst;
+    int F;
+    int mean;
+    const float* row_scale;
+    const float* addend;
+    long long ld_add;
+    const float* bias;
+    int epi;
+    int out_vec;
+    int n_pass;                        // passes over the feature axis (NS slabs each)
+};
+
+__device__ __forceinline__ float rows_epi(float v, int epi) {
+    if (epi & DGLLB_EPI_RELU) v = fmaxf(v, 0.f);
+    if (epi & DGLLB_EPI_ELU) v = v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+template <typename XT> struct RowsVec;
+template <> struct RowsVec<float> {
+    static constexpr int A = 4;        // elements per 128-bit load
+    typedef float4 raw_t;
+    __device__ static __forceinline__ raw_t load(const char* p) { return ldg_nc_f4(reinterpret_cast<const float*>(p)); }
+    __device__ static __forceinline__ void unpack(const raw_t& r, float* v) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+template <> struct RowsVec<__nv_bfloat16> {
+    static constexpr int A = 8;
+    typedef uint4 raw_t;
+    __device__ static __forceinline__ raw_t load(const char* p) { return ldg_nc_u4(p); }
+    __device__ static __forceinline__ void unpack(const raw_t& r, float* v) {
+        v[0] = bf16lo_to_f32(r.x); v[1] = bf16hi_to_f32(r.x); v[2] = bf16lo_to_f32(r.y); v[3] = bf16hi_to_f32(r.y);
+        v[4] = bf16lo_to_f32(r.z); v[5] = bf16hi_to_f32(r.z); v[6] = bf16lo_to_f32(r.w); v[7] = bf16hi_to_f32(r.w);
+    }
+};
+
+template <typename XT, int NS, int D, bool HAS_VALS, bool SHARDED>
+__global__ void __launch_bounds__(128)
+spmm_rows_kernel(const RowsParams p) {
+    typedef RowsVec<XT> V;
+    constexpr int A = V::A;
+    constexpr int W = 32 * A;                                   // elements per slab (512 bytes)
+    const int lane = threadIdx.x & 31;
+    const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long row = wid / p.n_pass;
+    if (row >= p.n_dst) return;
+    const int pass = static_cast<int>(wid - row * p.n_pass);
+    const int col0 = pass * NS * W + lane * A;                  // first column of this lane's slab 0
+    unsigned on = 0;                                            // bit s: slab s of this lane holds real columns
+#pragma unroll
+    for (int s = 0; s < NS; ++s) on |= (col0 + s * W < p.F) ? (1u << s) : 0u;
+    const long long lane_off = static_cast<long long>(col0) * static_cast<long long>(sizeof(XT));
+
+    long long beg, end;
+    if (p.rp64) {
+        beg = reinterpret_cast<const long long*>(p.row_ptr)[row];
+        end = reinterpret_cast<const long long*>(p.row_ptr)[row + 1];
+    } else {
+        beg = reinterpret_cast<const int*>(p.row_ptr)[row];
+        end = reinterpret_cast<const int*>(p.row_ptr)[row + 1];
+    }
+
+    float acc[NS][A];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int a = 0; a < A; ++a) acc[s][a] = 0.f;
+
+    for (long long e0 = beg; e0 < end; e0 += 32) {
+        const int n = static_cast<int>(min(32ll, end - e0));
+        // the lane that owns edge e0+lane resolves the source row's byte address once
+        const char* my_ptr = nullptr;
+        float my_w = 1.f;
+        if (lane < n) {
+            const int c = __ldg(p.col + e0 + lane);
+            if (SHARDED) {
+                const int sh = c / p.rows_per_shard;
+                my_ptr = p.shard_ptrs[sh] + static_cast<long long>(c - sh * p.rows_per_shard) * p.stride_bytes;
+            } else {
+                my_ptr = p.X + static_cast<long long>(c) * p.stride_bytes;
+            }
+            if (HAS_VALS) my_w = __ldg(p.vals + e0 + lane);
+        }
+        const unsigned long long my_addr = reinterpret_cast<unsigned long long>(my_ptr);
+
+        typename V::raw_t raw[D][NS];
+        float w[D];
+        // prologue: the first D edges
+#pragma unroll
+        for (int u = 0; u < D; ++u) {
+            if (u < n) {
+                const char* src = reinterpret_cast<const char*>(__shfl_sync(0xffffffffu, my_addr, u)) + lane_off;
+                if (HAS_VALS) w[u] = __shfl_sync(0xffffffffu, my_w, u);
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (on & (1u << s)) raw[u][s] = V::load(src + s * (W * static_cast<int>(sizeof(XT))));
+            }
+        }
+        // steady state: consume edge j, refill its slot with edge j + D
+        for (int j0 = 0; j0 < n; j0 += D) {
+#pragma unroll
+            for (int u = 0; u < D; ++u) {
+                const int j = j0 + u;
+                if (j < n) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        if (on & (1u << s)) {
+                            float v[A];
+                            V::unpack(raw[u][s], v);
+#pragma unroll
+                            for (int a = 0; a < A; ++a)
+                                acc[s][a] = HAS_VALS ? fmaf(w[u], v[a], acc[s][a]) : acc[s][a] + v[a];
+                        }
+                    }
+                    const int jn = j + D;
+                    if (jn < n) {
+                        const char* src = reinterpret_cast<const char*>(__shfl_sync(0xffffffffu, my_addr, jn)) + lane_off;
+                        if (HAS_VALS) w[u] = __shfl_sync(0xffffffffu, my_w, jn);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (on & (1u << s)) raw[u][s] = V::load(src + s * (W * static_cast<int>(sizeof(XT))));
+                    }
+                }
+            }
+        }
+    }
+
+    // epilogue: scale / addend / bias / activation / store
+    const long long deg = end - beg;
+    float scale = 1.f;
+    if (p.mean) scale = deg > 0 ? 1.f / static_cast<float>(deg) : 0.f;
+    if (p.row_scale) scale *= __ldg(p.row_scale + row);
+    const bool plain = !p.addend && !p.bias && !p.epi;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (!(on & (1u << s))) continue;
+        const int c0 = col0 + s * W;
+        const int valid = min(A, p.F - c0);
+        float* __restrict__ o = p.out + row * p.ldo + c0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            float v = acc[s][a] * scale;
+            if (!plain && a < valid) {
+                if (p.addend) v += __ldg(p.addend + row * p.ld_add + c0 + a);
+                if (p.bias) v += __ldg(p.bias + c0 + a);
+                v = rows_epi(v, p.epi);
+            }
+            acc[s][a] = v;
+        }
+        if (valid == A && p.out_vec) {
+#pragma unroll
+            for (int a = 0; a < A; a += 4)
+                stg_cs_f4(o + a, make_float4(acc[s][a], acc[s][a + 1], acc[s][a + 2], acc[s][a + 3]));
+        } else {
+#pragma unroll
+            for (int a = 0; a < A; ++a)
+                if (a < valid) o[a] = acc[s][a];
+        }
+    }
+}
+
+// block size (threads), slabs per warp and window depth can be pinned for A/B runs (options rows_tb/rows_ns/rows_d)
+struct RowsTuning { int tb, ns, depth; };
+static RowsTuning rows_tuning() { return {opt_get(OPT_ROWS_TB), opt_get(OPT_ROWS_NS), opt_get(OPT_ROWS_D)}; }
+
+template <typename XT, int NS, int D, bool HAS_VALS, bool SHARDED>
+static int rows_launch(const RowsParams& p, int tb, cudaStream_t st) {
+    const long long warps = p.n_dst * p.n_pass;
+    const long long blocks = (warps * 32 + tb - 1) / tb;
+    DGLLB_REQUIRE(blocks < (1ll << 31), "spmm_rows: grid too large (%lld blocks)", blocks);
+    spmm_rows_kernel<XT, NS, D, HAS_VALS, SHARDED><<<static_cast<unsigned>(blocks), tb, 0, st>>>(p);
+    DGLLB_LAUNCH_CHECK();
+    return DGLLB_OK;
+}
+
+template <typename XT, int NS, int D, bool SHARDED>
+static int rows_launch_v(const RowsParams& p, int tb, cudaStream_t st) {
+    return p.vals ? rows_launch<XT, NS, D, true, SHARDED>(p, tb, st) : rows_launch<XT, NS, D, false, SHARDED>(p, tb, st);
+}
+
+// NS slabs per warp and the window depth that goes with it (registers: NS*D*4 for the window + NS*A accumulators).
+// Measured on the headline block (F=602 fp32, 25-edge rows) and on F=128/256 blocks: profiles/r02_spmm_rows_sweep.md.
+template <typename XT, bool SHARDED>
+static int rows_dispatch(RowsParams& p, cudaStream_t st) {
+    constexpr int A = RowsVec<XT>::A;
+    const int n_slabs = (p.F + 32 * A - 1) / (32 * A);
+    const RowsTuning t = rows_tuning();
+    int max_ns = (t.ns >= 1 && t.ns <= 5) ? t.ns : (A == 4 ? 5 : 3);
+    p.n_pass = (n_slabs + max_ns - 1) / max_ns;
+    const int ns = (n_slabs + p.n_pass - 1) / p.n_pass;
+    const int tb = (t.tb == 32 || t.tb == 64 || t.tb == 128) ? t.tb : 64;
+    const int d = t.depth;
+    switch (ns) {
+        case 1: return d == 2 ? rows_launch_v<XT, 1, 2, SHARDED>(p, tb, st)
+                     : d == 8 ? rows_launch_v<XT, 1, 8, SHARDED>(p, tb, st)
+                              : rows_launch_v<XT, 1, 4, SHARDED>(p, tb, st);
+        case 2: return d == 2 ? rows_launch_v<XT, 2, 2, SHARDED>(p, tb, st)
+                     : d == 8 ? rows_launch_v<XT, 2, 8, SHARDED>(p, tb, st)
+                              : rows_launch_v<XT, 2, 4, SHARDED>(p, tb, st);
+        case 3: return d == 2 ? rows_launch_v<XT, 3, 2, SHARDED>(p, tb, st)
+                     : d == 5 ? rows_launch_v<XT, 3, 5, SHARDED>(p, tb, st)
+                              : rows_launch_v<XT, 3, 3, SHARDED>(p, tb, st);
+        case 4: return d == 2 ? rows_launch_v<XT, 4, 2, SHARDED>(p, tb, st)
+                     : d == 4 ? rows_launch_v<XT, 4, 4, SHARDED>(p, tb, st)
+                              : rows_launch_v<XT, 4, 3, SHARDED>(p, tb, st);
+        default: return d == 2 ? rows_launch_v<XT, 5, 2, SHARDED>(p, tb, st)
+                      : d == 3 ? rows_launch_v<XT, 5, 3, SHARDED>(p, tb, st)
+                               : rows_launch_v<XT, 5, 4, SHARDED>(p, tb, st);
+    }
+}
+
+// Entry used by spmm_run (spmm.cu) for short-row sum/mean aggregation over one table.
+int spmm_rows_try(const SpmmParams& sp, int x_dtype, cudaStream_t st) {
+    const int esz = x_dtype == DGLLB_F32 ? 4 : 2;
+    const int A = 16 / esz;
+    if (!sp.col || sp.row_cnt || sp.argmax || sp.F <= 16 * A) return DGLLB_ERR_UNSUPPORTED;
+    if (!aligned16(sp.X) || (sp.ldx % A) != 0) return DGLLB_ERR_UNSUPPORTED;
+    RowsParams p;
+    p.row_ptr = sp.row_ptr; p.rp64 = sp.rp64; p.col = sp.col; p.vals = sp.vals;
+    p.X = static_cast<const char*>(sp.X); p.stride_bytes = sp.ldx * esz;
+    p.shard_ptrs = nullptr; p.rows_per_shard = 1;
+    p.out = sp.out; p.ldo = sp.ldo; p.n_dst = sp.n_dst; p.F = sp.F; p.mean = sp.mean;
+    p.row_scale = sp.row_scale; p.addend = sp.addend; p.ld_add = sp.ld_add; p.bias = sp.bias; p.epi = sp.epi;
+    p.out_vec = aligned16(sp.out) && (sp.ldo % 4 == 0);
+    p.n_pass = 1;
+    return x_dtype == DGLLB_F32 ? rows_dispatch<float, false>(p, st) : rows_dispatch<__nv_bfloat16, false>(p, st);
+}
+
+}  // namespace dgllb
+
+using namespace dgllb;
+
+extern "C" int dgllb_spmm_csr_sharded(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                                      const float* values, const void* const* shard_ptrs, int n_shards,
+                                      int64_t rows_per_shard, int64_t stride_bytes, int x_dtype, float* out,
+                                      int64_t ldo, int64_t n_dst, int F, int reduce, void* stream) {
+    DGLLB_REQUIRE(n_dst >= 0 && F >= 0, "spmm_sharded: negative size");
+    if (n_dst == 0 || F == 0) return DGLLB_OK;
+    DGLLB_REQUIRE(row_ptr && col_idx && shard_ptrs && out, "spmm_sharded: null pointer");
+    DGLLB_REQUIRE(n_shards >= 1 && rows_per_shard >= 1 && rows_per_shard < (1ll << 31),
+                  "spmm_sharded: bad shard geometry");
+    DGLLB_REQUIRE(reduce == DGLLB_SUM || reduce == DGLLB_MEAN, "spmm_sharded: reduce must be sum or mean");
+    DGLLB_REQUIRE(x_dtype == DGLLB_F32 || x_dtype == DGLLB_BF16, "spmm_sharded: unknown dtype %d", x_dtype);
+    const int esz = x_dtype == DGLLB_F32 ? 4 : 2;
+    DGLLB_REQUIRE(stride_bytes % 16 == 0 && stride_bytes >= static_cast<int64_t>(F) * esz,
+                  "spmm_sharded: shard rows must be 16-byte multiples holding F elements (stride %lld, F %d)",
+                  (long long)stride_bytes, F);
+    DGLLB_REQUIRE(ldo >= F && n_dst < (1ll << 31), "spmm_sharded: bad output shape");
+    RowsParams p;
+    p.row_ptr = row_ptr; p.rp64 = row_ptr_is64; p.col = col_idx; p.vals = values;
+    p.X = nullptr; p.stride_bytes = stride_bytes;
+    p.shard_ptrs = reinterpret_cast<const char* const*>(shard_ptrs);
+    p.rows_per_shard = static_cast<int>(rows_per_shard);
+    p.out = out; p.ldo = ldo; p.n_dst = n_dst; p.F = F; p.mean = reduce == DGLLB_MEAN;
+    p.row_scale = nullptr; p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.epi = 0;
+    p.out_vec = aligned16(out) && (ldo % 4 == 0);
+    p.n_pass = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return x_dtype == DGLLB_F32 ? rows_dispatch<float, true>(p, st) : rows_dispatch<__nv_bfloat16, true>(p, st);
+}

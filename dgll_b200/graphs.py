@@ -98,6 +98,64 @@ def rmat_csr(n_nodes, nnz, seed=0, device="cuda", symmetric=False, index64=None)
     return row_ptr, col
 
 
+def _rmat_keys_into(buf, n_nodes, gen, device, chunk=1 << 26):
+    """Fill ``buf`` (int64) with dst*N+src keys of hash-permuted R-MAT edges, a chunk at a time; self loops get key -1."""
+    done = 0
+    while done < buf.numel():
+        m = min(chunk, buf.numel() - done)
+        src, dst, scale = _rmat_edges(n_nodes, m, gen, device, chunk=chunk)
+        src = _hash_perm(src, scale) % n_nodes
+        dst = _hash_perm(dst, scale, mult=0xC2B2AE35, add=0x27D4EB2F) % n_nodes
+        k = dst * n_nodes + src
+        k[src == dst] = -1
+        buf[done:done + m] = k
+        del src, dst, k
+        done += m
+
+
+def rmat_csr_large(n_nodes, nnz, seed=0, device="cuda"):
+    """``rmat_csr`` for graphs of billions of edges (papers100M-shaped: 1.6 B): the same generator, hash permutation,
+    self-loop and duplicate removal and uniform top-up, but keys are produced chunk-wise into ONE buffer and the surplus
+    is dropped by uniform thinning of the sorted keys, so the peak is ~4 key arrays (~50 GB at 1.6 B edges) instead of
+    ~10.  Returns (row_ptr int64[N+1], col_idx int32[nnz])."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    rounds = 0
+    while keys.numel() < nnz:
+        need = nnz - keys.numel()
+        extra = int(need * (1.2 if rounds == 0 else 1.5)) + 1024
+        buf = torch.empty(extra, dtype=torch.int64, device=device)
+        if rounds < 2:
+            _rmat_keys_into(buf, n_nodes, gen, device)
+        else:  # top up with uniform edges (R-MAT saturates its hot corner)
+            for o in range(0, extra, 1 << 27):
+                m = min(1 << 27, extra - o)
+                src = torch.randint(0, n_nodes, (m,), device=device, generator=gen)
+                dst = torch.randint(0, n_nodes, (m,), device=device, generator=gen)
+                k = dst * n_nodes + src
+                k[src == dst] = -1
+                buf[o:o + m] = k
+                del src, dst, k
+        if keys.numel():
+            buf = torch.cat([keys, buf])
+        del keys
+        keys = torch.unique(buf)
+        del buf
+        if keys.numel() and int(keys[0].item()) < 0:
+            keys = keys[1:]
+        rounds += 1
+    if keys.numel() > nnz:
+        # uniform thinning of the sorted key list: keep nnz entries at evenly spaced ranks
+        idx = torch.div(torch.arange(nnz, device=device, dtype=torch.int64) * keys.numel(), nnz, rounding_mode="floor")
+        keys = keys[idx]
+        del idx
+    col = (keys % n_nodes).to(torch.int32)
+    keys = torch.div(keys, n_nodes, rounding_mode="floor")
+    row_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=device)
+    torch.cumsum(torch.bincount(keys, minlength=n_nodes), 0, out=row_ptr[1:])
+    return row_ptr, col
+
+
 def uniform_csr(n_nodes, deg, seed=0, device="cuda"):
     """Control graph: every row has exactly ``deg`` uniform random in-neighbours (duplicates allowed)."""
     gen = torch.Generator(device=device).manual_seed(seed)

@@ -14,6 +14,9 @@ from ._lib import (BF16, EPI_ELU, EPI_RELU, F32, GAT_EXP_NEG, GAT_SOFTMAX, MAX, 
 
 _REDUCE = {"sum": SUM, "add": SUM, "mean": MEAN, "max": MAX}
 
+set_option = _lib.set_option
+get_option = _lib.get_option
+
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 _raw_device = getattr(torch._C, "_cuda_getDevice", None)
@@ -131,6 +134,35 @@ def spmm_csr(row_ptr, col_idx, x, values=None, reduce="sum", n_dst=None, out=Non
                                x.size(0), (col.numel() if col is not None else -1), F, red, _p(row_scale), _p(addend), ld_add, _p(bias), epi,
                                _p(argmax), plan._h if plan is not None else None, _stream()), "spmm_csr")
     return (out, argmax) if return_argmax else out
+
+
+def spmm_csr_sharded(row_ptr, col_idx, shard_ptrs, rows_per_shard, stride_bytes, F, dtype=torch.float32, values=None,
+                     reduce="mean", n_dst=None, out=None):
+    """Sum/mean aggregation straight from a node-range-partitioned table: ``shard_ptrs`` is a device int64 tensor of
+    shard base addresses (``parallel.PeerShardedTable.shard_ptrs``), column ids are GLOBAL row ids.  fp32 result."""
+    _need_cuda(row_ptr, col_idx, shard_ptrs, values, out)
+    rp, is64 = _rowptr(row_ptr)
+    n_dst = rp.numel() - 1 if n_dst is None else n_dst
+    col = _index32(col_idx, "col_idx")
+    if dtype == torch.float32:
+        xd = F32
+    elif dtype == torch.bfloat16:
+        xd = BF16
+    else:
+        raise TypeError("table dtype must be float32 or bfloat16")
+    if reduce not in ("sum", "mean"):
+        raise ValueError("spmm_csr_sharded: reduce must be 'sum' or 'mean'")
+    if out is None:
+        out = torch.empty((n_dst, F), dtype=torch.float32, device=rp.device)
+    o, ldo = _rowmajor(out, "out")
+    if o is not out:
+        raise ValueError("out must have contiguous rows")
+    if values is not None:
+        values = values.to(torch.float32).contiguous()
+    check(lib().dgllb_spmm_csr_sharded(_p(rp), is64, _p(col), _p(values), _p(shard_ptrs), shard_ptrs.numel(),
+                                       int(rows_per_shard), int(stride_bytes), xd, _p(out), ldo, n_dst, int(F),
+                                       _REDUCE[reduce], _stream()), "spmm_csr_sharded")
+    return out
 
 
 def sddmm_csr(row_ptr, col_idx, a, b):

@@ -113,6 +113,22 @@ class SAGEConv(F.nn.Module):
             F.init.xavier_uniform_(self.fc_self.weight, gain=gain)
         F.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
+    def forward_preaggregated(self, h_neigh_mean, feat_dst):
+        """The layer applied to an input-feature neighbour MEAN computed upstream (``h_neigh_mean`` [n_dst, in]) and
+        the destination rows ``feat_dst`` [n_dst, >= in]: ``W_self x_dst + W_neigh mean_j x_j + b``.  The mean of raw
+        input features does not depend on the weights, so a pipelined trainer aggregates mini-batch i+1 — straight from
+        the (possibly partitioned) feature table — while step i trains (``dgll_b200.pipelined``).  Same result as
+        ``forward`` up to the order of the linear map and the mean (DGL's ``lin_before_mp`` choice)."""
+        if self._aggre_type != "mean":
+            raise ValueError("forward_preaggregated: 'mean' aggregator only")
+        rst = ops.linear(feat_dst[:, :self._in_dst_feats], self.fc_self.weight, trans_w=True, bias=self.bias) + \
+            ops.linear(h_neigh_mean, self.fc_neigh.weight, trans_w=True)
+        if self.activation is not None:
+            rst = self.activation(rst)
+        if self.norm is not None:
+            rst = self.norm(rst)
+        return rst
+
     def forward(self, block, feat, feat_table=None):
         """``feat`` = h_src or (h_src, h_dst).  With ``feat_table`` (layer 0) the neighbour mean is taken straight
         from the global table through ``block.col_global`` and only the dst rows are gathered."""

@@ -52,11 +52,15 @@ class GraphSAGE(F.nn.Module):
         self.dropout = F.nn.Dropout(dropout)
         self.activation = activation
 
-    def forward(self, blocks, x, feat_table=None):
-        assert isinstance(blocks, list) and blocks[0].is_block
+    def forward(self, blocks, x, feat_table=None, pre=None):
+        """``pre=(neigh_mean, feat_dst)``: layer 0's input-feature neighbour mean and destination rows were produced
+        upstream (``SAGEConv.forward_preaggregated``); ``blocks[0]`` is then unused and may be ``None``."""
+        assert isinstance(blocks, list) and (pre is not None or blocks[0].is_block)
         h = x
         for l, (layer, block) in enumerate(zip(self.layers, blocks)):
-            if l == 0 and feat_table is not None:
+            if l == 0 and pre is not None:
+                h = layer.forward_preaggregated(pre[0], pre[1])
+            elif l == 0 and feat_table is not None:
                 h = layer(block, None, feat_table=feat_table)
             else:
                 h = layer(block, h)

@@ -109,13 +109,14 @@ class GraphedSageTrainer:
     the all-reduce) run eagerly after the replay."""
 
     def __init__(self, model, opt, table, labels, batch_size=1024, fanouts=(25, 10), group=None, precision=None,
-                 n_feat=None, capture_collectives=False):
+                 n_feat=None, capture_collectives=False, label_offset=0):
         if len(fanouts) != 2 or len(model.layers) != 2:
             raise ValueError("GraphedSageTrainer: 2-layer models / two fanouts")
         if table is None and n_feat is None:
             raise ValueError("GraphedSageTrainer: pass the resident feature table, or n_feat for per-batch feature rows")
         dev = labels.device if table is None else table.device
         self.model, self.opt, self.table, self.labels, self.group = model, opt, table, labels, group
+        self.label_offset = int(label_offset)   # labels may be this rank's slice of a node-range partition
         self.B = int(batch_size)
         self.cap_d0 = self.B * (1 + int(fanouts[-1]))
         self.cap_e0 = self.cap_d0 * int(fanouts[0])
@@ -140,8 +141,8 @@ class GraphedSageTrainer:
         self._precision = precision
         world = parallel.dist.get_world_size(group) if parallel.dist.is_initialized() else 1
         self._opt_in_graph = world == 1 and bool(opt.defaults.get("capturable", False))
-        # DRAFT (round 2): with more than one rank, capture the gradient all-reduce (NCCL is graph-capturable) and the
-        # optimizer too.  Gradients live in ONE flat buffer (p.grad are views): zeroed, accumulated into by autograd,
+        # With more than one rank and capture_collectives, the gradient all-reduce (NCCL is graph-capturable) and the
+        # optimizer are captured too.  Gradients live in ONE flat buffer (p.grad are views): zeroed, accumulated into by autograd,
         # all-reduced in place; the 1/world average is folded into the loss scale.  One launch per step on every rank.
         self._world = world
         self._flat = None
@@ -263,7 +264,7 @@ class GraphedSageTrainer:
             logits = self.model(self._blocks(), None, feat_table=self.table)
         else:
             logits = self.model(self._blocks(), self.x)
-        target = torch.where(self.valid, self.labels[self.seeds.clamp(min=0)], torch.full_like(self.seeds, -100))
+        target = torch.where(self.valid, self.labels[(self.seeds - self.label_offset).clamp(min=0)], torch.full_like(self.seeds, -100))
         loss = torch.nn.functional.cross_entropy(logits, target, ignore_index=-100)
         if self._flat is not None:
             self._flat.zero_()

@@ -64,6 +64,16 @@ int dgllb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_b
 /* Number of kernels this library has launched on this process (all threads).
  * bench.py reads it to report `gpu_launches`. */
 int64_t dgllb_launch_count(void);
+/*
+ * Tuning options (kernel family pins, block sizes, NVTX on/off).  Each option is an integer that starts from the
+ * environment variable DGLLB_<NAME> (read ONCE per process) and is changed afterwards only here; no launch path calls
+ * getenv().  `value` is a decimal integer or one of the option's words; NULL / "" / "auto" = library default.
+ *   spmm_kernel  auto | rowsplit | stream | wholerow        gat_kernel  auto | group | row
+ *   spmm_tb, rows_tb, rows_ns, rows_d, gat_row_warps, gat_bwd_tb, bin_tb, gemm_kernel   integers (0 = default)
+ *   nvtx         1 = NVTX ranges around the entry points named like the reference's (FeatureCache/storage.py:164-206)
+ */
+int dgllb_set_option(const char* name, const char* value);
+int dgllb_get_option(const char* name, int* value_out);
 
 /* ---------------------------------------------------- CSR aggregation -- */
 
@@ -119,6 +129,21 @@ int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx
                    int reduce, const float* row_scale, const float* addend,
                    int64_t ld_add, const float* bias, int epilogue,
                    int32_t* argmax_out, const dgllb_csr_plan* plan, void* stream);
+
+/*
+ * The same sum/mean aggregation with the source table node-range PARTITIONED over the GPUs of one NVSwitch box and read
+ * in place: row id c lives in shard c / rows_per_shard at local row c % rows_per_shard; shard_ptrs[n_shards] is a DEVICE
+ * array of the shards' base addresses (the local shard and the peers' shards mapped with dgllb_ipc_import).  The halo
+ * exchange of SURVEY.md §8(e) — bucket ids by owner, all_to_all ids, owner-side gather, all_to_all rows, un-permute —
+ * becomes the aggregation kernel's own 128-bit loads over NVLink; nothing is staged or read back.  With n_shards == 1
+ * it is the fused gather+aggregation over a resident table (dgll/data/dgraph.py:105 + the mean of
+ * GPU Accelerator/CommGNNModel.py:72-77).  stride_bytes must be a multiple of 16.  No plan: rows are expected short
+ * (sampled blocks); no epilogue.
+ */
+int dgllb_spmm_csr_sharded(const void* row_ptr, int row_ptr_is64, const int32_t* col_idx,
+                           const float* values, const void* const* shard_ptrs, int n_shards,
+                           int64_t rows_per_shard, int64_t stride_bytes, int x_dtype, float* out,
+                           int64_t ldo, int64_t n_dst, int F, int reduce, void* stream);
 
 /*
  * SDDMM: out_e[e] = < A[row(e), 0:F], B[col_idx[e], 0:F] > for every CSR edge.
@@ -193,6 +218,8 @@ int dgllb_gather_rows_cached(const void* cache_table, int64_t cache_stride_bytes
  * dgllb_ipc_import).  Replaces, for the partitioned table, the gather of dgll/data/dgraph.py:105 and the
  * host/RPC feature fetch of FeatureCache/storage.py:101-126 — no collective, no host read-back
  * (SURVEY.md §8 e "P2P-map all shards and let the gather kernel issue remote 128-bit loads").
+ * A NEGATIVE id is a padding slot of a fixed-capacity id array (dgllb_build_block_cap): nothing is read, the output
+ * row is zero-filled.
  */
 int dgllb_gather_rows_sharded(const void* const* shard_ptrs, int n_shards, int64_t rows_per_shard,
                               int64_t stride_bytes, const void* ids, int ids_is64, void* out,

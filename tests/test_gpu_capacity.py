@@ -1,6 +1,5 @@
 """Fixed-capacity sampler / block builder (negative ids = padding, nothing read back) and the training step with the
-sampler captured inside the CUDA graph.  DRAFT written without GPU access at the end of round 1: to be run, fixed and
-measured at the start of round 2."""
+sampler captured inside the CUDA graph (verified on the B200 at the start of round 2)."""
 import copy
 
 import numpy as np

@@ -27,15 +27,12 @@ def reddit():
 
 
 def _with_kernel(name, fn):
-    old = os.environ.get("DGLLB_SPMM_KERNEL")
-    os.environ["DGLLB_SPMM_KERNEL"] = name
+    from dgll_b200 import kernels
+    kernels.set_option("spmm_kernel", name)
     try:
         return fn()
     finally:
-        if old is None:
-            os.environ.pop("DGLLB_SPMM_KERNEL", None)
-        else:
-            os.environ["DGLLB_SPMM_KERNEL"] = old
+        kernels.set_option("spmm_kernel", None)
 
 
 def test_full_reddit_spmm_properties(K, reddit):
@@ -172,11 +169,11 @@ def test_full_products_gat_properties(K):
         assert bool(torch.isfinite(rmax[nz]).all()) and bool((rsum[nz] > 0).all())
     wh = torch.randn((Np, heads * D), device="cuda", generator=g)
     a = K.gat_forward(rp, col, wh, el, er, heads, 0.2, plan=plan)
-    os.environ["DGLLB_GAT_KERNEL"] = "group"
+    K.set_option("gat_kernel", "group")
     try:
         b = K.gat_forward(rp, col, wh, el, er, heads, 0.2)
     finally:
-        os.environ.pop("DGLLB_GAT_KERNEL", None)
+        K.set_option("gat_kernel", None)
     assert (a - b).abs().max().item() <= 1e-5 * max(a.abs().max().item(), 1.0)
     del b, ones
     # zero attention vectors => every neighbour weighs 1/deg: the fused GAT layer IS the mean aggregation, forward and

@@ -293,9 +293,9 @@ def test_gat_forward_parity(K, heads, D, mode):
 
 
 @pytest.mark.parametrize("heads,D", [(4, 64), (1, 256), (4, 128), (2, 48)])
-def test_gat_whole_row_kernel_matches_oracle(K, heads, D, monkeypatch):
-    """DGLLB_GAT_KERNEL=row pins the one-warp-per-row (all heads) forward kernel."""
-    monkeypatch.setenv("DGLLB_GAT_KERNEL", "row")
+def test_gat_whole_row_kernel_matches_oracle(K, heads, D, gat_kernel):
+    """Option gat_kernel=row pins the one-warp-per-row (all heads) forward kernel."""
+    gat_kernel("row")
     rng = np.random.default_rng(heads * 7 + D)
     n = 500
     rp, col = rand_csr(rng, n, n, 45, heavy=[(7, 600)])
@@ -307,10 +307,10 @@ def test_gat_whole_row_kernel_matches_oracle(K, heads, D, monkeypatch):
         out, rmax, rsum = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, elu=True,
                                         save_stats=True)
         assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
-        monkeypatch.setenv("DGLLB_GAT_KERNEL", "group")
+        gat_kernel("group")
         out2, rmax2, rsum2 = K.gat_forward(dev(rp), dev(col), dev(wh), dev(el), dev(er), heads, 0.2, mode=mode,
                                            elu=True, save_stats=True)
-        monkeypatch.setenv("DGLLB_GAT_KERNEL", "row")
+        gat_kernel("row")
         assert torch.equal(rmax, rmax2) and rel_err(rsum.cpu().numpy(), rsum2.cpu().numpy()) <= FP32_TOL
         # long rows split into chunks, partial softmax states merged
         plan = K.CsrPlan(dev(rp), chunk_edges=100)
@@ -599,13 +599,33 @@ def test_ppi_golden_layer_on_device(K):
 
 
 # ------------------------------------------------ SpMM kernel families -----
-@pytest.mark.parametrize("family", ["rowsplit", "stream", "bulk"])
+@pytest.fixture
+def gat_kernel(K):
+    yield lambda name: K.set_option("gat_kernel", name)
+    K.set_option("gat_kernel", None)
+
+
+@pytest.fixture
+def spmm_family(K):
+    """Pin one SpMM kernel family through the library's option table for the duration of a test."""
+    def pin(name, **opts):
+        K.set_option("spmm_kernel", name)
+        for k, v in opts.items():
+            K.set_option(k, v)
+    yield pin
+    for k in ("spmm_kernel", "rows_tb", "rows_ns", "rows_d", "spmm_tb"):
+        K.set_option(k, None)
+
+
+@pytest.mark.parametrize("family", ["rowsplit", "stream", "wholerow", "wholerow:ns2", "wholerow:ns3:d8"])
 @pytest.mark.parametrize("F,ld,dt", [(602, 604, "f32"), (256, 256, "f32"), (128, 128, "f32"), (100, 100, "f32"),
-                                     (602, 608, "bf16"), (1000, 1000, "f32"), (36, 36, "f32")])
-def test_spmm_kernel_families_agree_with_oracle(K, family, F, ld, dt, monkeypatch):
-    """DGLLB_SPMM_KERNEL pins the one-warp-per-row, the rolling-LDG streaming or the TMA-staged kernel: all three
-    must match the oracle on ragged blocks (empty rows, short rows, one long row, rows straddling chunk borders)."""
-    monkeypatch.setenv("DGLLB_SPMM_KERNEL", family)
+                                     (602, 608, "bf16"), (1000, 1000, "f32"), (36, 36, "f32"), (1500, 1504, "bf16")])
+def test_spmm_kernel_families_agree_with_oracle(K, family, F, ld, dt, spmm_family):
+    """Option spmm_kernel pins the (row, slab)-per-warp, the rolling-LDG streaming or the whole-row rolling-window
+    kernel (with its slabs-per-warp / window-depth variants): all must match the oracle on ragged blocks (empty rows,
+    short rows, one long row, rows straddling chunk borders)."""
+    parts = family.split(":")
+    spmm_family(parts[0], **{("rows_ns" if o.startswith("ns") else "rows_d"): int(o.lstrip("nsd")) for o in parts[1:]})
     rng = np.random.default_rng(F + len(family))
     n_dst, n_src = 2500, 4000
     rp, col = rand_csr(rng, n_dst, n_src, 37, heavy=[(5, 1500), (2499, 300)], empty_frac=0.15)
@@ -636,9 +656,9 @@ def test_spmm_kernel_families_agree_with_oracle(K, family, F, ld, dt, monkeypatc
     assert rel_err(out.cpu().numpy(), np.broadcast_to(bias, (n_dst, F))) <= tol
 
 
-@pytest.mark.parametrize("family", ["rowsplit", "stream", "bulk"])
-def test_spmm_families_deterministic(K, family, monkeypatch):
-    monkeypatch.setenv("DGLLB_SPMM_KERNEL", family)
+@pytest.mark.parametrize("family", ["rowsplit", "stream", "wholerow"])
+def test_spmm_families_deterministic(K, family, spmm_family):
+    spmm_family(family)
     g = torch.Generator(device="cuda").manual_seed(1)
     n, F = 20000, 602
     deg = torch.randint(0, 40, (n,), device="cuda", generator=g)
@@ -750,6 +770,52 @@ def test_gather_rows_sharded_bit_exact(K, F, dtype):
     assert torch.equal(t.fetch(ids), full[ids])
 
 
+@pytest.mark.parametrize("F,dtype", [(128, torch.float32), (602, torch.float32), (100, torch.float32),
+                                     (602, torch.bfloat16), (1000, torch.float32), (40, torch.float32)])
+def test_spmm_csr_sharded_equals_oracle_and_single_table(K, F, dtype):
+    """The aggregation that reads a node-range-partitioned table in place (the halo fetch fused into the SpMM): same
+    numbers as the oracle and as the single-table kernel, for sum/mean, with and without edge values, ragged rows."""
+    rng = np.random.default_rng(F)
+    n_src, n_dst, P = 9001, 1200, 4
+    part = (n_src + P - 1) // P
+    ld = (F + 3) // 4 * 4 if dtype == torch.float32 else (F + 7) // 8 * 8
+    rp, col = rand_csr(rng, n_dst, n_src, 30, heavy=[(3, 700)], empty_frac=0.1)
+    x = rng.standard_normal((n_src, F)).astype(np.float32)
+    full = padded(x, ld).to(dtype)
+    xr = full[:, :F].float().cpu().numpy()
+    vals = rng.random(col.size).astype(np.float32) + 0.1
+    shards = [full[r * part:min(n_src, (r + 1) * part)].clone() for r in range(P)]
+    ptrs = torch.tensor([s.data_ptr() for s in shards], dtype=torch.int64, device="cuda")
+    sb = ld * full.element_size()
+    for rpt in (np.int64, np.int32):
+        for red in ("sum", "mean"):
+            for v in (None, vals):
+                ref = oracle.spmm_csr(rp, col, xr, values=v, reduce=red)
+                out = K.spmm_csr_sharded(dev(rp.astype(rpt)), dev(col), ptrs, part, sb, F, dtype=dtype,
+                                         values=None if v is None else dev(v), reduce=red)
+                assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL, (red, v is not None)
+    one = torch.tensor([full.data_ptr()], dtype=torch.int64, device="cuda")
+    a = K.spmm_csr_sharded(dev(rp), dev(col), one, n_src, sb, F, dtype=dtype)
+    b = K.spmm_csr_sharded(dev(rp), dev(col), ptrs, part, sb, F, dtype=dtype)
+    assert torch.equal(a, b)                                   # the shard lookup does not change the arithmetic
+    with pytest.raises(Exception):
+        K.spmm_csr_sharded(dev(rp), dev(col), ptrs, part, sb + 4, F, dtype=dtype)   # rows must be 16-byte multiples
+
+
+def test_library_options_roundtrip(K):
+    K.set_option("spmm_kernel", "stream")
+    assert K.get_option("spmm_kernel") == 2
+    K.set_option("spmm_kernel", None)
+    assert K.get_option("spmm_kernel") == 0
+    K.set_option("rows_d", 5)
+    assert K.get_option("rows_d") == 5
+    K.set_option("rows_d", None)
+    with pytest.raises(Exception):
+        K.set_option("no_such_option", 1)
+    with pytest.raises(Exception):
+        K.set_option("spmm_kernel", "no_such_family")
+
+
 def test_ipc_export_import_roundtrip_same_process(K):
     """The IPC handle of a tensor's allocation + offset names the same bytes (cudaIpcOpenMemHandle cannot be opened in
     the exporting process, so only the export side and the offset arithmetic are checked here; the cross-process
@@ -792,10 +858,10 @@ def test_device_block_builder_matches_sort_based_compaction(K, fanouts):
 # ------------------------------------------------------ attention dropout --
 @pytest.mark.parametrize("kernel", ["group", "row"])
 @pytest.mark.parametrize("mode", ["softmax", "exp_neg"])
-def test_gat_attention_dropout_forward_backward_with_replayed_mask(K, kernel, mode, monkeypatch):
+def test_gat_attention_dropout_forward_backward_with_replayed_mask(K, kernel, mode, gat_kernel):
     """The kernels' dropout mask is exported (dgllb_gat_dropout_mask) and replayed in an fp64 autograd restatement of
     gatconv.py:30-54 / :111-148 WITH dropout on the attention coefficients: outputs and all three gradients match."""
-    monkeypatch.setenv("DGLLB_GAT_KERNEL", kernel)
+    gat_kernel(kernel)
     rng = np.random.default_rng(3)
     n, heads, D, pdrop, seed = 300, 4, 32, 0.4, 123456789
     rp, col = rand_csr(rng, n, n, 25, heavy=[(9, 400)])

@@ -40,7 +40,7 @@ def main():
                     help="graph = the training step replayed as one CUDA graph on fixed-capacity buffers "
                          "(train.GraphedSageTrainer); eager = Python-dispatched step")
     ap.add_argument("--capture-collectives", action="store_true",
-                    help="DRAFT (round 2): capture the flat gradient all-reduce and Adam inside the step graph (N > 1)")
+                    help="capture the flat gradient all-reduce and Adam inside the step graph (N > 1)")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="graph mode: produce step i+1 (sample, build blocks, fetch rows) on the main stream instead of a "
                          "side stream that runs under the replay of step i")

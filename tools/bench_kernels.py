@@ -73,15 +73,15 @@ def main():
             out = torch.empty((N, (Fw + 3) // 4 * 4), device=dev)[:, :Fw]
             nbytes = NNZ * (4 + Fw * b) + N * (Fw * 4 + 8)
             plan = K.CsrPlan(rp, chunk_edges=4096)
-            for fam in ("rowsplit", "stream", "bulk"):
-                os.environ["DGLLB_SPMM_KERNEL"] = fam
+            for fam in ("rowsplit", "stream", "wholerow"):
+                K.set_option("spmm_kernel", fam)
                 ms = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=Fw), args.iters)
                 report("spmm_full_graph[%s]" % fam, "F=%d %s" % (Fw, str(dt).split(".")[-1]), ms, nbytes)
-            os.environ["DGLLB_SPMM_KERNEL"] = "rowsplit"
+            K.set_option("spmm_kernel", "rowsplit")
             ms = timeit(lambda: K.spmm_csr(rp, col, x, reduce="mean", out=out, F=Fw, plan=plan), args.iters)
             report("spmm_full_graph[rowsplit+plan]", "F=%d %s" % (Fw, str(dt).split(".")[-1]), ms, nbytes,
                    {"heavy_rows": plan.n_heavy_rows, "chunks": plan.n_chunks})
-            os.environ.pop("DGLLB_SPMM_KERNEL", None)
+            K.set_option("spmm_kernel", None)
             del x, out
 
     if "gather" in which:
@@ -123,11 +123,11 @@ def main():
             b0, b1 = G.sample_blocks(rp, col, seeds, (25, 10), rng_seed=9)
             out = torch.empty((b0.num_dst, 604), device=dev)[:, :F]
             nbytes = b0.num_edges() * (4 + F * 4) + b0.num_dst * (F * 4 + 4)
-            for fam in ("rowsplit", "stream", "bulk"):
-                os.environ["DGLLB_SPMM_KERNEL"] = fam
+            for fam in ("rowsplit", "stream", "wholerow"):
+                K.set_option("spmm_kernel", fam)
                 ms = timeit(lambda: K.spmm_csr(b0.row_ptr, b0.col_global, table, reduce="mean", out=out, F=F), 30)
                 report("spmm_block0[%s]" % fam, "batch=%d n_dst=%d nnz=%d" % (batch, b0.num_dst, b0.num_edges()), ms, nbytes)
-            os.environ.pop("DGLLB_SPMM_KERNEL", None)
+            K.set_option("spmm_kernel", None)
         del table
 
     if "gemm" in which:
@@ -169,20 +169,20 @@ def main():
         nbytes = nnz * (4 + heads * D * 4 + heads * 4) + Np * (heads * D * 4 + heads * 4 + 8)
         gplan = K.CsrPlan(rp, chunk_edges=1024)
         for fam in ("group", "row"):
-            os.environ["DGLLB_GAT_KERNEL"] = fam
+            K.set_option("gat_kernel", fam)
             ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out), args.iters)
             report("gat_forward[%s] (fused SDDMM+softmax+SpMM)" % fam, "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes)
-        os.environ.pop("DGLLB_GAT_KERNEL", None)
+        K.set_option("gat_kernel", None)
         ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out, plan=gplan), args.iters)
         report("gat_forward[row + plan 1024]", "products-shaped N=%d nnz=%d heads=4 D=64" % (Np, nnz), ms, nbytes,
                {"heavy_rows": gplan.n_heavy_rows, "chunks": gplan.n_chunks})
         gplan256 = K.CsrPlan(rp, chunk_edges=256)
         for warps in ("8", "4", "1"):
-            os.environ["DGLLB_GAT_ROW_WARPS"] = warps
+            K.set_option("gat_row_warps", warps)
             ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out, plan=gplan256), args.iters)
             report("gat_forward[row + plan 256, %s warp(s) per block]" % warps, "products-shaped", ms, nbytes,
                    {"heavy_rows": gplan256.n_heavy_rows, "chunks": gplan256.n_chunks})
-        os.environ.pop("DGLLB_GAT_ROW_WARPS", None)
+        K.set_option("gat_row_warps", None)
         ms = timeit(lambda: K.spmm_csr(rp, col, wh, reduce="sum", out=out), args.iters)
         report("spmm_full_graph (same graph, F=256)", "products-shaped", ms, nnz * (4 + 256 * 4) + Np * (256 * 4 + 8))
         # backward: pass 1 over the CSR (alpha, dz per edge), pass 2 over the transposed CSR (d_Wh, d_er)
