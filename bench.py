@@ -368,7 +368,7 @@ def extra_partitioned(args, rank, world, dev, barrier):
            "train_seeds": n_train, "scaling": "weak per step (1,024 seeds per GPU); the epoch is the fixed 1,207,179 seeds",
            "setup_s": round(setup_s, 1), "mechanisms": {}}
 
-    def run_peer(tbl, tag):
+    def run_peer(tbl, tag, row_ptr=row_ptr, col=col):
         sharded = P.PeerShardedTable(N, tbl)
         torch.manual_seed(args.seed)
         model = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
@@ -383,7 +383,7 @@ def extra_partitioned(args, rank, world, dev, barrier):
         barrier()
         halo = tr.halo_stats()
         stage = tr.stage_times(seeds[:24 * BATCH], steps=24)
-        t = torch.tensor([r["time_s"], stage["produce_ms_eager"], stage["train_ms_eager"], halo["remote_edge_fraction"],
+        t = torch.tensor([r["time_s"], stage["produce_ms"], stage["train_ms"], halo["remote_edge_fraction"],
                           float(halo["remote_bytes_per_step"])], device=dev, dtype=torch.float64)
         mx = t.clone()
         if world > 1:
@@ -398,7 +398,7 @@ def extra_partitioned(args, rank, world, dev, barrier):
                "epoch_s": round(mx[0].item(), 4), "batches_per_gpu": n_b,
                "ms_per_step": round(mx[0].item() * 1e3 / n_b, 4),
                "seeds_per_s": round(world * per_rank / mx[0].item(), 1),
-               "stage_ms_unoverlapped": {"sample+halo+aggregate (branch B)": round(mx[1].item(), 4),
+               "stage_ms_alone": {"sample+halo+aggregate (branch B)": round(mx[1].item(), 4),
                                          "fwd+bwd+all-reduce+Adam (branch A)": round(mx[2].item(), 4)},
                "remote_edge_fraction_measured": round(t[3].item(), 4),
                "nvlink_bytes_in_per_gpu_per_step": int(t[4].item()), "loss": round(r["loss"], 4)}
@@ -444,8 +444,25 @@ def extra_partitioned(args, rank, world, dev, barrier):
         for p in model.parameters():
             p.grad = None
 
+    def run_uniform_control():
+        """Same N, nnz, features and trainer on the uniform-random control graph (SURVEY.md §8 d): every node has 14-15
+        in-neighbours, so blocks are full-size and nearly every sampled source row is distinct — the heaviest halo load
+        this model can put on NVLink (the R-MAT graph's random seeds mostly have tiny in-degree)."""
+        g = torch.Generator(device=dev).manual_seed(args.seed)
+        deg = torch.full((N,), NNZ // N, dtype=torch.int64, device=dev)
+        deg[: NNZ - (NNZ // N) * N] += 1
+        u_rp = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(deg, 0, out=u_rp[1:])
+        del deg
+        u_col = torch.empty(NNZ, dtype=torch.int32, device=dev)
+        for o in range(0, NNZ, 1 << 28):
+            m = min(1 << 28, NNZ - o)
+            u_col[o:o + m] = torch.randint(0, N, (m,), device=dev, generator=g, dtype=torch.int32)
+        run_peer(table, "peer_fp32_uniform_control_graph", u_rp, u_col)
+
     for tag, fn in (("peer_fp32", lambda: run_peer(table, "peer_fp32")), ("nccl_all_to_all", run_nccl),
-                    ("peer_bf16_table", lambda: run_peer(table.to(torch.bfloat16), "peer_bf16_table"))):
+                    ("peer_bf16_table", lambda: run_peer(table.to(torch.bfloat16), "peer_bf16_table")),
+                    ("peer_fp32_uniform_control_graph", run_uniform_control)):
         try:
             fn()
         except Exception as ex:

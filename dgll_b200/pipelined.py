@@ -103,6 +103,7 @@ class PipelinedSageTrainer:
         self.loss = torch.zeros((), device=dev)
         self.loss_sum = torch.zeros((), device=dev)
         self.graphs = None
+        self._g_train = None
         self._side = None
 
     # ------------------------------------------------------------------------------------------ branch B --
@@ -239,27 +240,35 @@ class PipelinedSageTrainer:
                 "loss": float(self.loss_sum.item()) / max(n, 1)}
 
     def stage_times(self, seeds, steps=20):
-        """Device time of the two branches run one after the other (eagerly, on the current stream) — the numbers behind
-        the ``stage_ms`` of bench.py's partitioned extra.  Trains ``steps`` mini-batches as a side effect."""
+        """Device time of each branch ALONE, replayed as its own CUDA graph (no overlap, no Python dispatch) — the
+        numbers behind the ``stage_ms`` of bench.py's partitioned extra.  Trains ``steps`` steps on one mini-batch as a
+        side effect; call it after the measured epochs."""
         self.set_seeds(seeds)
-        prev = None
-        if self._precision is not None:
-            prev = ops.get_gemm_precision()
-            ops.set_gemm_precision(self._precision)
+        if self.graphs is None:
+            self.capture()
+        if getattr(self, "_g_train", None) is None:
+            prev = None
+            if self._precision is not None:
+                prev = ops.get_gemm_precision()
+                ops.set_gemm_precision(self._precision)
+            self._g_train = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_train):
+                self._train(self.slots[0])
+            if prev is not None:
+                ops.set_gemm_precision(prev)
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        self._prologue.replay()
         torch.cuda.synchronize()
         for i in range(steps):
             ev[i][0].record()
-            self._produce(self.slots[0])
+            self._prologue.replay()                           # branch B: the next mini-batch into slot 0
             ev[i][1].record()
-            self._train(self.slots[0])
+            self._g_train.replay()                            # branch A on slot 0
             ev[i][2].record()
         torch.cuda.synchronize()
-        if prev is not None:
-            ops.set_gemm_precision(prev)
         pm = sorted(e[0].elapsed_time(e[1]) for e in ev)[steps // 2]
         tm = sorted(e[1].elapsed_time(e[2]) for e in ev)[steps // 2]
-        return {"produce_ms_eager": pm, "train_ms_eager": tm}
+        return {"produce_ms": pm, "train_ms": tm}
 
     def halo_stats(self):
         """Measured share of the input layer's source rows that live on another GPU, from the last produced slot
