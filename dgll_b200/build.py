@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdgll_b200.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 SOURCES = [
-    "runtime.cu", "spmm.cu", "spmm_rows.cu", "gather.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "gemm.cu",
+    "runtime.cu", "spmm.cu", "spmm_rows.cu", "gather.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "gemm_tf32.cu", "gemm.cu",
     "transpose.cu", "legacy.cu", "gat.cu", "binspmm.cu", "sampler.cu", "peer.cu", "block.cu", "layerwise.cu",
 ]
 NVCC_FLAGS = [

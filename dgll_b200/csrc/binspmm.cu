@@ -39,6 +39,54 @@ binarize_pack_kernel(const float* __restrict__ X, long long ldx, uint32_t* __res
     if (lane == 0) packed[item] = word;
 }
 
+// Vector path (X 16-byte aligned, ldx % 4 == 0): a warp owns U consecutive (row, 128-feature) items; each lane loads one
+// float4 per item (512 contiguous bytes per warp-load, U of them in flight), turns it into a 4-bit nibble, and the 8
+// lanes that share a 32-feature word OR their nibbles together with 3 xor-shuffles.  A streaming read: HBM bound.
+// (The first version — one warp per (row, word), one 128-byte load per warp, ballot — reached 1.2 TB/s.)
+template <int U>
+__global__ void __launch_bounds__(256)
+binarize_pack_vec_kernel(const float* __restrict__ X, long long ldx, uint32_t* __restrict__ packed,
+                         long long wpr, long long n_items, int items_per_row, int F) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long it0 = warp * U; it0 < n_items; it0 += n_warps * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long it = it0 + u;
+            v[u] = make_float4(-1.f, -1.f, -1.f, -1.f);
+            if (it < n_items) {
+                const long long r = it / items_per_row;
+                const int f = static_cast<int>(it - r * items_per_row) * 128 + lane * 4;
+                const float* src = X + r * ldx + f;
+                if (f + 4 <= F) {
+                    v[u] = ldg_nc_f4(src);
+                } else if (f < F) {                 // ragged tail of the row: 1..3 real features
+                    v[u].x = __ldg(src);
+                    if (f + 1 < F) v[u].y = __ldg(src + 1);
+                    if (f + 2 < F) v[u].z = __ldg(src + 2);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long it = it0 + u;
+            uint32_t nib = (v[u].x >= 0.f ? 1u : 0u) | (v[u].y >= 0.f ? 2u : 0u) | (v[u].z >= 0.f ? 4u : 0u) |
+                           (v[u].w >= 0.f ? 8u : 0u);
+            uint32_t w = nib << (4 * (lane & 7));
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+            if (it < n_items && (lane & 7) == 0) {
+                const long long r = it / items_per_row;
+                const int c = static_cast<int>(it - r * items_per_row);
+                packed[r * wpr + c * 4 + (lane >> 3)] = w;
+            }
+        }
+    }
+}
+
 // ---- bit-sliced (carry-save) formulation -------------------------------------------------------------------
 // One warp per destination row; LANE l OWNS PACKED WORD l of every neighbour row, so a neighbour costs one
 // coalesced load of its whole packed row (wpr*4 contiguous bytes) instead of 32 lanes touching 32 different rows.
@@ -216,6 +264,21 @@ extern "C" int dgllb_binarize_pack(const float* X, int64_t ldx, uint32_t* packed
     if (n_rows == 0 || words_per_row == 0) return DGLLB_OK;
     DGLLB_REQUIRE(X && packed, "binarize_pack: null pointer");
     DGLLB_REQUIRE(words_per_row * 32 >= F && ldx >= F, "binarize_pack: words_per_row*32 < F or ldx < F");
+    if (aligned16(X) && ldx % 4 == 0 && words_per_row % 4 == 0) {
+        DevInfo di;
+        int rc = get_devinfo(&di);
+        if (rc != DGLLB_OK) return rc;
+        constexpr int U = 4;
+        const int ipr = static_cast<int>(words_per_row / 4);
+        const long long n_items = n_rows * ipr;
+        long long blocks = ((n_items + U - 1) / U * 32 + 255) / 256;
+        const long long cap = static_cast<long long>(di.sm_count) * 8 * 2;   // 8 resident CTAs per SM, two waves
+        if (blocks > cap) blocks = cap;
+        binarize_pack_vec_kernel<U><<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            X, ldx, packed, words_per_row, n_items, ipr, F);
+        DGLLB_LAUNCH_CHECK();
+        return DGLLB_OK;
+    }
     const long long items = n_rows * words_per_row;
     const long long blocks = (items * 32 + 255) / 256;
     DGLLB_REQUIRE(blocks < (1ll << 31), "binarize_pack: grid too large");

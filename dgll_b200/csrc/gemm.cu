@@ -13,8 +13,10 @@ extern "C" int dgllb_gemm_f32(const float* A, int64_t lda, int transA, const flo
     DGLLB_REQUIRE(C && (K == 0 || (A && B)), "gemm: null pointer");
     DGLLB_REQUIRE(ldc >= N, "gemm: ldc < N");
     DGLLB_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gemm: leading dimension too small");
-    DGLLB_REQUIRE(precision == 0 || precision == 1, "gemm: unknown precision %d", precision);
+    DGLLB_REQUIRE(precision >= 0 && precision <= 2, "gemm: unknown precision %d", precision);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == 2)
+        return gemm_tf32(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
     if (precision == 1)
         return gemm_tcgen05(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
     return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);

@@ -1,0 +1,451 @@
+// gemm_tf32.cu — the dense per-layer transform on tcgen05 tensor cores straight from the fp32 tensors in HBM.
+//
+// Replaces torch.mm(x, W) (dgll/nn/Convolution/gcnconv.py:30, gatconv.py:117, Evaluation/PPI/gcn_model.py:70) and its
+// autograd products dX = G W^T, dW = X^T G when the caller asks for precision = 2 (TF32 operands, fp32 accumulation in
+// TMEM; <= 2e-3 of max|ref|).  Round 1's tensor-core path (gemm_tcgen05.cu, precision = 1) first PACKED both operands
+// to bf16 with a separate launch; ncu showed the layer shapes bound by that pass (160,000 x 602 x 256: 0.385 ms, of
+// which 0.24 ms packing; profiles/r01_gemm_tcgen05.txt).  Here nothing is converted or copied:
+//   * TMA (cp.async.bulk.tensor.2d, 128B swizzle) loads fp32 boxes of A and B as they lie in memory; tcgen05.mma
+//     kind::tf32 reads the fp32 words (10-bit mantissa, low bits ignored) — M=128, N=128, K=8 per instruction;
+//   * an operand whose reduction axis is contiguous is loaded K-major (box 32 k x 128 rows); an operand stored the
+//     other way round ([K, rows]: the X^T and G^T of a backward pass, or a [K, N] weight) is loaded MN-major (four
+//     boxes of 32 rows x 32 k, TMA swizzle 128B_ATOM_32B = the one MN-major layout tcgen05 accepts for 32-bit operands)
+//     and the instruction descriptor's a_major / b_major bit tells the tensor core — no transposition pass either;
+//   * CTAs of the same 128-row block of A are adjacent in launch order (blockIdx.x walks N first), so the second
+//     128-column tile finds A in L2 and HBM moves A once;
+//   * deterministic split-K (fixed-order reduction kernel) for the long-reduction / few-tile shapes (dW = X^T G).
+// Pipeline per CTA (one 128 x 128 tile; 2 CTAs per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b.x32 -> (+C) + bias -> ReLU/ELU -> 128-bit stores).
+// An operand TMA cannot address (base not 16-byte aligned, or row stride not a multiple of 16 bytes — e.g. a [256, 602]
+// nn.Linear weight) is first copied into an aligned fp32 workspace by align_copy_kernel (small operands in practice).
+// Roofline: HBM for the layer shapes of this path (K <= 1,204, N <= 256): bytes = 4*(M*K + N*K + M*N); tensor pipe
+// (TF32 = half the bf16 rate) only for large square products, where precision = 1 remains the faster choice.
+#include "common.cuh"
+#include "internal.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace dgllb {
+
+namespace tf32 {
+
+constexpr int BM = 128, BN = 128, BK = 32, kStages = 3;      // BK fp32 = 128 bytes = one swizzle row
+constexpr int kThreads = 256;
+constexpr int kStageA = BM * BK * 4, kStageB = BN * BK * 4;  // 16 KB each
+constexpr int kTmemCols = 128;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, tf32 x tf32 -> fp32
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Shared-memory matrix descriptor (descriptor version 1).
+//   K-major  : layout type 2 (SWIZZLE_128B): rows of 128 bytes along K, 8-row groups 1024 B apart -> SBO = 1024, LBO unused
+//   MN-major : 32-bit operands have ONE legal MN-major layout, type 1 (SWIZZLE_128B with a 32-byte swizzle base; what TMA
+//              writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 32 fp32 along MN (128 B) x 4 k-rows (512 B);
+//              the next 4 k-rows follow at SBO = 512 B (consecutive rows of one TMA box), the next 32 MN elements at
+//              LBO = 4096 B (the next TMA box).  One K=8 instruction spans two such atoms.
+__device__ __forceinline__ uint64_t make_desc(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_u32(smem_ptr) & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout) << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float epi_fn(float v, int epi) {
+    if (epi & DGLLB_EPI_RELU) v = fmaxf(v, 0.f);
+    if (epi & DGLLB_EPI_ELU) v = v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+// A_MN / B_MN: the operand is stored with its MN axis contiguous ([K, rows]) and loaded MN-major.
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 float* __restrict__ C, long long ldc, long long M, int N, int n_tiles_n, int num_kb_total,
+                 int kb_per_split, long long split_slab, const float* __restrict__ bias, int epi, int accumulate) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem_a = smem;
+    unsigned char* smem_b = smem + kStages * kStageA;
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+    __shared__ uint32_t tmem_base_holder;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // N tiles of one 128-row block of A are adjacent in launch order: the second finds A in L2
+    const int tile_n = blockIdx.x % n_tiles_n;
+    const long long tile_m = blockIdx.x / n_tiles_n;
+    const int m0 = static_cast<int>(tile_m * BM), n0 = tile_n * BN;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int num_kb = min(kb_per_split, num_kb_total - kb0);
+    C += static_cast<long long>(blockIdx.z) * split_slab;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_holder, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], kStageA + kStageB);
+                const int k0 = (kb0 + kb) * BK;
+                unsigned char* sa = smem_a + s * kStageA;
+                unsigned char* sb = smem_b + s * kStageB;
+                if (A_MN) {
+#pragma unroll
+                    for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmap_a, m0 + b * 32, k0, &full_bar[s]);
+                } else {
+                    tma_load_2d(sa, &tmap_a, k0, m0, &full_bar[s]);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int b = 0; b < BN / 32; ++b) tma_load_2d(sb + b * 4096, &tmap_b, n0 + b * 32, k0, &full_bar[s]);
+                } else {
+                    tma_load_2d(sb, &tmap_b, k0, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = f32 (bit 4), A = B = TF32 (2 at [7,10) and [10,13)), a_major bit 15, b_major
+            // bit 16 (1 = MN-major), N/8 at [17,23), M/16 at [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u) |
+                                   (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t da = A_MN ? make_desc(smem_a + s * kStageA, 4096, 512, 1) : make_desc(smem_a + s * kStageA, 16, 1024, 2);
+                const uint64_t db = B_MN ? make_desc(smem_b + s * kStageB, 4096, 512, 1) : make_desc(smem_b + s * kStageB, 16, 1024, 2);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    // 8 tf32 along K: K-major = 32 bytes inside the swizzled row (+2 in 16-byte units);
+                    //                 MN-major = the next 8 k-rows (+1024 bytes = +64)
+                    tc_mma_tf32(tmem_base, da + static_cast<uint64_t>((A_MN ? 64 : 2) * k),
+                                db + static_cast<uint64_t>((B_MN ? 64 : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(&empty_bar[s]);
+            }
+            tc_commit(&tmem_full_bar);
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const long long row = static_cast<long long>(m0) + q * 32 + lane;
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                            (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            if (n0 + c * 32 >= N) break;
+            uint32_t r[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+            if (row < M) {
+                float* crow = C + row * ldc;
+                const int cbase = n0 + c * 32;
+                if (vec_ok && cbase + 32 <= N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        if (accumulate) {
+                            const float4 o = *reinterpret_cast<const float4*>(crow + cbase + j);
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        if (bias) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cbase + j));
+                            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                        }
+                        v.x = epi_fn(v.x, epi); v.y = epi_fn(v.y, epi);
+                        v.z = epi_fn(v.z, epi); v.w = epi_fn(v.w, epi);
+                        *reinterpret_cast<float4*>(crow + cbase + j) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = cbase + j;
+                        if (col < N) {
+                            float v = __uint_as_float(r[j]);
+                            if (accumulate) v += crow[col];
+                            if (bias) v += __ldg(bias + col);
+                            crow[col] = epi_fn(v, epi);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// dst[r, 0:cols] = src[r, 0:cols], dst row stride ldd (a multiple of 4 floats), pad columns zero
+__global__ void __launch_bounds__(256)
+align_copy_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd, long long rows,
+                  int cols) {
+    const long long total = rows * ldd;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / ldd;
+        const int c = static_cast<int>(i - r * ldd);
+        dst[i] = c < cols ? __ldg(src + r * lds + c) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, long long slab, int splits, float* __restrict__ C, long long ldc,
+                     long long M, int N, int ldp, const float* __restrict__ bias, int epi, int accumulate) {
+    const long long total = M * N;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / N;
+        const int c = static_cast<int>(i - r * N);
+        float v = accumulate ? C[r * ldc + c] : 0.f;
+        const float* p = part + r * ldp + c;
+        for (int z = 0; z < splits; ++z) v += p[z * slab];
+        if (bias) v += __ldg(bias + c);
+        C[r * ldc + c] = epi_fn(v, epi);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// fp32 tensor stored [outer, inner] row-major with row stride ld (elements).  Box = box_inner x box_outer, 128B swizzle,
+// out-of-bounds elements read as zero (K and M/N tails).
+static int make_tmap(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_inner,
+                     int box_outer, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("gemm: cuTensorMapEncodeTiled is not available from the driver");
+        return DGLLB_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", static_cast<int>(r), inner,
+                  outer, ld);
+        return DGLLB_ERR_CUDA;
+    }
+    return DGLLB_OK;
+}
+
+static bool tma_ok(const float* p, long long ld) {
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 4) == 0;
+}
+
+template <bool A_MN, bool B_MN>
+static cudaError_t set_smem_attr(size_t smem) {
+    return cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem));
+}
+
+template <bool A_MN, bool B_MN>
+static void launch(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, float* C,
+                   long long ldc, long long M, int N, int n_tiles_n, int num_kb, int kb_per, long long slab,
+                   const float* bias, int epi, int accumulate) {
+    gemm_tf32_kernel<A_MN, B_MN><<<grid, kThreads, smem, st>>>(ta, tb, C, ldc, M, N, n_tiles_n, num_kb, kb_per, slab,
+                                                               bias, epi, accumulate);
+}
+
+}  // namespace tf32
+
+int gemm_tf32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+              long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
+              cudaStream_t st) {
+    using namespace tf32;
+    if (K == 0 || N >= (1ll << 31) || K >= (1ll << 30) || M >= (1ll << 31)) {
+        return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epi, accumulate, st);
+    }
+    DevInfo di;
+    { int rc_ = get_devinfo(&di); if (rc_ != DGLLB_OK) return rc_; }
+    // operands TMA cannot address are copied into an aligned workspace first (stored shape: rows x cols)
+    const long long a_rows = transA ? K : M, a_cols = transA ? M : K;
+    const long long b_rows = transB ? N : K, b_cols = transB ? K : N;
+    const bool fix_a = !tma_ok(A, lda), fix_b = !tma_ok(B, ldb);
+    const long long lda2 = (a_cols + 3) / 4 * 4, ldb2 = (b_cols + 3) / 4 * 4;
+    const size_t bytes_a = fix_a ? ((static_cast<size_t>(a_rows) * lda2 * 4 + 255) & ~static_cast<size_t>(255)) : 0;
+    const size_t bytes_b = fix_b ? ((static_cast<size_t>(b_rows) * ldb2 * 4 + 255) & ~static_cast<size_t>(255)) : 0;
+    char* ws = nullptr;
+    float* part = nullptr;
+    int rc = DGLLB_OK;
+    do {
+        if (bytes_a + bytes_b) {
+            cudaError_t e = cudaMallocAsync(&ws, bytes_a + bytes_b, st);
+            if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
+            const long long cap = static_cast<long long>(di.sm_count) * 8;
+            if (fix_a) {
+                float* d = reinterpret_cast<float*>(ws);
+                long long nb = (a_rows * lda2 + 255) / 256;
+                align_copy_kernel<<<static_cast<unsigned>(nb > cap ? cap : nb), 256, 0, st>>>(A, lda, d, lda2, a_rows,
+                                                                                             static_cast<int>(a_cols));
+                g_launch_count.fetch_add(1);
+                A = d;
+                lda = lda2;
+            }
+            if (fix_b) {
+                float* d = reinterpret_cast<float*>(ws + bytes_a);
+                long long nb = (b_rows * ldb2 + 255) / 256;
+                align_copy_kernel<<<static_cast<unsigned>(nb > cap ? cap : nb), 256, 0, st>>>(B, ldb, d, ldb2, b_rows,
+                                                                                             static_cast<int>(b_cols));
+                g_launch_count.fetch_add(1);
+                B = d;
+                ldb = ldb2;
+            }
+        }
+        // A operand (rows = M): stored [M, K] -> K-major box 32 (k) x 128 (rows); stored [K, M] -> MN-major boxes 32 x 32
+        // B operand (rows = N): stored [N, K] (transB) -> K-major; stored [K, N] -> MN-major
+        const bool a_mn = transA != 0, b_mn = transB == 0;
+        CUtensorMap ta, tb;
+        const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+        if ((rc = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK, sw_mn) : make_tmap(&ta, A, K, M, lda, BK, BM, sw_k)) != DGLLB_OK) break;
+        if ((rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK, sw_mn) : make_tmap(&tb, B, K, N, ldb, BK, BN, sw_k)) != DGLLB_OK) break;
+        const size_t smem = static_cast<size_t>(kStages) * (kStageA + kStageB) + 1024;
+        static std::once_flag attr_once[64];
+        static cudaError_t attr_err[64];
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        const int slot = dev_id & 63;
+        std::call_once(attr_once[slot], [&]() {
+            cudaError_t e = set_smem_attr<false, false>(smem);
+            if (e == cudaSuccess) e = set_smem_attr<false, true>(smem);
+            if (e == cudaSuccess) e = set_smem_attr<true, false>(smem);
+            if (e == cudaSuccess) e = set_smem_attr<true, true>(smem);
+            attr_err[slot] = e;
+        });
+        if (attr_err[slot] != cudaSuccess) {
+            set_error("gemm: %s", cudaGetErrorString(attr_err[slot]));
+            rc = DGLLB_ERR_CUDA;
+            break;
+        }
+        const long long tiles_m = (M + BM - 1) / BM;
+        const int tiles_n = static_cast<int>((N + BN - 1) / BN);
+        const long long tiles = tiles_m * tiles_n;
+        if (tiles >= (1ll << 31)) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: too many tiles"); break; }
+        dim3 grid(static_cast<unsigned>(tiles), 1, 1);
+        const int num_kb = static_cast<int>((K + BK - 1) / BK);
+        int splits = 1, kb_per = num_kb;
+        if (tiles * 2 <= di.sm_count && num_kb >= 16) {
+            long long want = di.sm_count / tiles;
+            if (want > 32) want = 32;
+            if (want > num_kb / 8) want = num_kb / 8;
+            if (want >= 2) {
+                kb_per = static_cast<int>((num_kb + want - 1) / want);
+                splits = (num_kb + kb_per - 1) / kb_per;
+            }
+        }
+        float* out = C;
+        long long ldo = ldc, slab = 0;
+        const float* kb_bias = bias;
+        int kepi = epi, kacc = accumulate;
+        if (splits > 1) {
+            const int ldp = static_cast<int>((N + 3) / 4 * 4);
+            slab = M * ldp;
+            cudaError_t e = cudaMallocAsync(&part, sizeof(float) * static_cast<size_t>(slab) * splits, st);
+            if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
+            grid.z = static_cast<unsigned>(splits);
+            out = part; ldo = ldp; kb_bias = nullptr; kepi = 0; kacc = 0;
+        }
+        const int Ni = static_cast<int>(N);
+        if (a_mn && b_mn) launch<true, true>(grid, smem, st, ta, tb, out, ldo, M, Ni, tiles_n, num_kb, kb_per, slab, kb_bias, kepi, kacc);
+        else if (a_mn) launch<true, false>(grid, smem, st, ta, tb, out, ldo, M, Ni, tiles_n, num_kb, kb_per, slab, kb_bias, kepi, kacc);
+        else if (b_mn) launch<false, true>(grid, smem, st, ta, tb, out, ldo, M, Ni, tiles_n, num_kb, kb_per, slab, kb_bias, kepi, kacc);
+        else launch<false, false>(grid, smem, st, ta, tb, out, ldo, M, Ni, tiles_n, num_kb, kb_per, slab, kb_bias, kepi, kacc);
+        g_launch_count.fetch_add(1);
+        if (splits > 1) {
+            long long rb = (M * N + 255) / 256;
+            if (rb > static_cast<long long>(di.sm_count) * 8) rb = static_cast<long long>(di.sm_count) * 8;
+            splitk_reduce_kernel<<<static_cast<unsigned>(rb), 256, 0, st>>>(part, slab, splits, C, ldc, M, Ni,
+                                                                            static_cast<int>(ldo), bias, epi, accumulate);
+            g_launch_count.fetch_add(1);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("gemm: launch failed: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
+    } while (0);
+    if (part) cudaFreeAsync(part, st);
+    if (ws) cudaFreeAsync(ws, st);
+    return rc;
+}
+
+}  // namespace dgllb

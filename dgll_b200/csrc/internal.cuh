@@ -59,4 +59,9 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
                  float* C, long long ldc, long long M, long long N, long long K, const float* bias, int epi,
                  int accumulate, cudaStream_t st);
 
+// tcgen05 TF32 GEMM straight from the fp32 tensors (gemm_tf32.cu): TMA loads, K-major or MN-major operands, no packing
+int gemm_tf32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+              long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
+              cudaStream_t st);
+
 }  // namespace dgllb

@@ -14,6 +14,7 @@ pinned once), or an object exposing the reference's ``_node_frame._frame[name].d
 """
 import torch
 
+from .. import _nvtx
 from .. import kernels as K
 
 
@@ -74,14 +75,10 @@ class GraphCacheServer:
     def get_feat_from_server(self, nids, embed_names, to_gpu=False):
         """storage.py:101-126 — rows ``nid_map[nids]`` of the host tables (host tensors unless ``to_gpu``)."""
         nids_in_full = self.nid_map[nids.to(self.device)]
-        if to_gpu:
-            return {name: K.gather_rows(self._device_view(name), nids_in_full) for name in embed_names}
         idx = nids_in_full.cpu()
+        if to_gpu:     # storage.py:120-122: host-side index, then an asynchronous copy to the device
+            return {name: self._host_table(name)[idx].to(self.device, non_blocking=True) for name in embed_names}
         return {name: self._host_table(name)[idx] for name in embed_names}
-
-    def _device_view(self, name):
-        """The host table as seen from the device: pinned memory is addressable in place (UVA)."""
-        return self._host_table(name)
 
     def auto_cache(self, dgl_g, embed_names, capability=None):
         """storage.py:64-98.  ``dgl_g``: anything with ``out_degrees()`` or a degree tensor."""
@@ -150,14 +147,22 @@ class GraphCacheServer:
             self.fetch_from_cache(nodeflow)
             return
         for i in range(nodeflow.num_layers):
-            nodeflow._node_frames[i] = self.fetch(nodeflow.layer_parent_nid(i))
+            with _nvtx.range("cache-idxload"):
+                tnid = nodeflow.layer_parent_nid(i).to(self.device)
+            # the reference's cache-index / cache-allocate / cache-gpu / cache-cpu stages (:170-192) are ONE kernel here
+            with _nvtx.range("cache-gpu+cache-cpu"):
+                frame = self.fetch(tnid)
+            with _nvtx.range("cache-asign"):
+                nodeflow._node_frames[i] = frame
 
     def fetch_from_cache(self, nodeflow):
         """storage.py:201-210."""
         for i in range(nodeflow.num_layers):
-            tnid = nodeflow.layer_parent_nid(i).to(self.device)
-            nodeflow._node_frames[i] = {name: K.gather_rows(self.gpu_fix_cache[name], tnid)
-                                        for name in self.gpu_fix_cache}
+            with _nvtx.range("cache-idxload"):
+                tnid = nodeflow.layer_parent_nid(i).to(self.device)
+            with _nvtx.range("cache-gpu"):
+                nodeflow._node_frames[i] = {name: K.gather_rows(self.gpu_fix_cache[name], tnid)
+                                            for name in self.gpu_fix_cache}
 
     def log_miss_rate(self, miss_num, total_num):
         self.try_num += total_num

@@ -79,6 +79,61 @@ def _fixed_fanout_graph(batch, k, device):
     return ops.CsrGraph(rp, col, n_src=batch * k)
 
 
+class BinGCNConv(F.nn.Module):
+    """Binarized-feature GCN layer (the "Quantization/Binarization" feature the reference names in README.md:11 and its
+    architecture diagram but ships no code for; BASELINE.json configs[3]; semantics SURVEY.md §8 a18):
+
+        h_i = ( mean_{j in N(i)} sign(x_j) ) W + b,        sign(x) = +1 for x >= 0, -1 otherwise
+
+    The aggregation runs on the bit-packed popcount SpMM (``dgllb_binarize_pack`` + ``dgllb_bin_spmm_csr``): 4 bytes
+    per 32 features per edge instead of 128, integer-exact counts.  Aggregation comes first (the binarized rows are
+    the cheap thing to move), the dense transform second.  Backward: straight-through estimator — the sign is treated as
+    the identity where ``|x| <= ste_clip`` (``None`` = everywhere) — so dL/dx is ONE transposed aggregation on the fp32
+    SpMM kernels; W and b get their ordinary gradients.  ``adj``: anything ``ops.as_csr`` takes (edge values are
+    ignored: the binarized mean is over the unweighted neighbourhood)."""
+
+    def __init__(self, in_features, out_features, bias=True, ste_clip=1.0):
+        super().__init__()
+        self.in_features, self.out_features, self.ste_clip = in_features, out_features, ste_clip
+        self.weight = F.Parameter(torch.empty(in_features, out_features))
+        if bias:
+            self.bias = F.Parameter(torch.empty(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, adj):
+        agg = ops.binarized_aggregate_ste(adj, x, clip=self.ste_clip)
+        return ops.linear(agg, self.weight, bias=self.bias)
+
+    def __repr__(self):
+        return "%s (%d -> %d)" % (self.__class__.__name__, self.in_features, self.out_features)
+
+
+class BinGCN(F.nn.Module):
+    """Two ``BinGCNConv`` layers stacked the way ``GCN`` stacks ``gcnConv`` (gcnconv.py:43-58):
+    relu -> dropout -> layer -> log_softmax."""
+
+    def __init__(self, in_features, nhid, nclass, dropout, ste_clip=1.0):
+        super().__init__()
+        self.in_features, self.nhid, self.nclass, self.dropout = in_features, nhid, nclass, dropout
+        self.gcn1 = BinGCNConv(in_features, nhid, ste_clip=ste_clip)
+        self.gcn2 = BinGCNConv(nhid, nclass, ste_clip=ste_clip)
+
+    def forward(self, x, adj):
+        h1 = Fn.relu(self.gcn1(x, adj))
+        h1_d = Fn.dropout(h1, self.dropout, training=self.training)
+        # centre the hidden activations before taking their sign: after a ReLU every feature would binarize to +1
+        logits = self.gcn2(h1_d - h1_d.mean(dim=0, keepdim=True), adj)
+        return Fn.log_softmax(logits, dim=1)
+
+
 class NeighborAggregator(F.nn.Module):
     """sageconv.py:10-45 — reduce over the K axis (mean / sum / max), then ``@ W`` (+ b)."""
 

@@ -20,10 +20,10 @@ _PRECISION = {"gemm": "fp32"}
 
 
 def set_gemm_precision(p):
-    """'fp32' = exact SIMT fp32 FMA (parity path, <=1e-5); 'bf16' = tcgen05 tensor cores, bf16 operands with fp32
-    accumulation in TMEM (<=1e-2)."""
-    if p not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    """'fp32' = exact SIMT fp32 FMA (parity path, <=1e-5); 'tf32' = tcgen05 tensor cores reading the fp32 operands in
+    place (TF32, fp32 accumulation in TMEM, <=2e-3); 'bf16' = tcgen05 on operands packed to bf16 (<=1e-2)."""
+    if p not in ("fp32", "bf16", "tf32"):
+        raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
     _PRECISION["gemm"] = p
 
 
@@ -401,6 +401,41 @@ def binarized_aggregate(adj, x=None, packed=None, F=None, mode="mean"):
         F = x.size(1)
     plan = graph.bin_plan()
     return K.bin_spmm_csr(graph.row_ptr, graph.col, packed, F, mode=mode, n_dst=graph.n_dst, plan=plan)
+
+
+class _BinAggFn(torch.autograd.Function):
+    """mean_{j in N(i)} sign(x_j) on the bit-packed popcount kernel, with the straight-through estimator in backward:
+    d sign(x)/dx := 1 where |x| <= clip (everywhere when clip is None), so dL/dx = A_mean^T g masked by |x| <= clip —
+    one transposed aggregation on the fp32 SpMM kernels."""
+
+    @staticmethod
+    def forward(ctx, x, graph, clip):
+        packed = K.binarize_pack(x)
+        out = K.bin_spmm_csr(graph.row_ptr, graph.col, packed, x.size(1), mode="mean", n_dst=graph.n_dst,
+                             plan=graph.bin_plan())
+        ctx.graph, ctx.clip = graph, clip
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (x,) = ctx.saved_tensors
+        graph = ctx.graph
+        g = grad.contiguous() * graph.inv_degrees()[:, None]
+        gt = graph.transpose()
+        gx = K.spmm_csr(gt.row_ptr, gt.col, g, reduce="sum", n_dst=gt.n_dst, plan=gt.plan())
+        if ctx.clip is not None:
+            gx = gx * (x.abs() <= ctx.clip)
+        return gx, None, None
+
+
+def binarized_aggregate_ste(adj, x, clip=1.0):
+    """Differentiable binarized mean aggregation (README.md:11): forward = ``binarized_aggregate(...,
+    mode='mean')`` of the sign bits of ``x``; backward = straight-through estimator (see ``_BinAggFn``)."""
+    graph = as_csr(adj, binary=True)
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _BinAggFn.apply(x, graph, clip)
+    return binarized_aggregate(graph, x=x, mode="mean")
 
 
 # ----------------------------------------------------------------- gather ---

@@ -8,6 +8,7 @@ import time
 
 import torch
 
+from . import _nvtx
 from . import graphs as G
 from . import ops, parallel
 
@@ -45,17 +46,19 @@ def sage_epoch(model, opt, table, labels, n_feat, row_ptr=None, col_idx=None, se
     n = 0
     it = batches if batches is not None else range(0, seeds.numel(), batch_size)
     for b, item in enumerate(it):
-        if batches is not None:
-            s, blocks = item
-        else:
-            s = seeds[item:item + batch_size]
-            blocks = G.sample_blocks(row_ptr, col_idx, s, fanouts, rng_seed=rng_seed * 7919 + b)
-        logits = model(blocks, None, feat_table=table)   # padded table: SAGEConv slices the logical width itself
-        loss = torch.nn.functional.cross_entropy(logits, labels[s])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        parallel.allreduce_gradients(params, group=group)
-        opt.step()
+        with _nvtx.range("gpu-load"):                    # FeatureCache/gcn.py:83-87 (sampling + feature fetch)
+            if batches is not None:
+                s, blocks = item
+            else:
+                s = seeds[item:item + batch_size]
+                blocks = G.sample_blocks(row_ptr, col_idx, s, fanouts, rng_seed=rng_seed * 7919 + b)
+        with _nvtx.range("gpu-compute"):                 # FeatureCache/gcn.py:88-93
+            logits = model(blocks, None, feat_table=table)   # padded table: SAGEConv slices the logical width itself
+            loss = torch.nn.functional.cross_entropy(logits, labels[s])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            parallel.allreduce_gradients(params, group=group)
+            opt.step()
         loss_sum += loss.detach()
         n += 1
     e1.record()

@@ -239,8 +239,11 @@ int dgllb_ipc_release(void* dev_ptr, int64_t offset);
 /*
  * C[M,N] = epi( A[M,K] . B[K,N] + bias[N] ), all row-major fp32 in HBM.
  * precision 0: exact fp32 FMA (SIMT) — the parity path (<=1e-5 rel);
- * precision 1: tcgen05 tensor cores, bf16 operands (converted on the fly),
- *              fp32 accumulate in TMEM — the fast path (<=1e-2 rel).
+ * precision 1: tcgen05 tensor cores, bf16 operands (packed by a pre-pass),
+ *              fp32 accumulate in TMEM (<=1e-2 rel); the faster choice for large square products;
+ * precision 2: tcgen05 tensor cores, TF32 operands read by TMA straight from the fp32 tensors (no packing, no
+ *              transposition: operands stored the other way round are loaded MN-major), fp32 accumulate in TMEM
+ *              (<=2e-3 rel) — the fast path for the layer shapes of this path, which are bound by HBM traffic.
  * transA / transB: use A^T (A stored [K,M]) / B^T (B stored [N,K]).
  * Replaces torch.mm(x, W) gcnconv.py:30, gcn_model.py:70, gatconv.py:117 and the
  * per-edge recomputed transform of gcn_fused_kernel.cu:46-54.

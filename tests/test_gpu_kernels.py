@@ -254,6 +254,9 @@ def test_binarize_and_bin_spmm_bit_exact(K, F):
     packed = K.binarize_pack(dev(x))
     ref_packed = oracle.binarize_pack(x)
     assert np.array_equal(packed.cpu().numpy().view(np.uint32), ref_packed)
+    # 16-byte rows (the layout of the feature tables): the vectorised streaming pack, incl. a ragged row tail
+    packed_v = K.binarize_pack(padded(x, (F + 3) // 4 * 4 + 4)[:, :F])
+    assert np.array_equal(packed_v.cpu().numpy().view(np.uint32), ref_packed)
     ref_cnt = oracle.bin_spmm_counts(rp, col, ref_packed, F)
     cnt = K.bin_spmm_csr(dev(rp), dev(col), packed, F, mode="count").cpu().numpy()
     assert cnt.dtype == np.int32 and np.array_equal(cnt, ref_cnt)
@@ -670,6 +673,60 @@ def test_spmm_families_deterministic(K, family, spmm_family):
     a = K.spmm_csr(rp, col, x, reduce="mean", F=F)
     b = K.spmm_csr(rp, col, x, reduce="mean", F=F)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------- tcgen05 TF32 GEMM --
+TF32_TOL = 2e-3
+
+
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (300, 64, 50), (1000, 256, 602), (17, 5, 3), (4096, 41, 256),
+                                    (129, 130, 65), (2000, 256, 1204), (11264, 172, 256), (257, 300, 4096)])
+def test_gemm_tcgen05_tf32_parity_all_orientations(K, M, N, K_):
+    """precision='tf32': TMA loads the fp32 operands as they lie in memory (K-major or MN-major), tcgen05.mma kind::tf32
+    accumulates in TMEM.  All four storage orientations, epilogue, accumulate, ragged M/N/K, operands whose rows are not
+    16-byte multiples (aligned-copy fallback) and the deterministic split-K shape.  Bar: 2e-3 of max|ref| against the
+    fp64 product of the fp32 operands; the result does not depend on how the operands are stored."""
+    rng = np.random.default_rng(M + 3 * N)
+    a = rng.standard_normal((M, K_)).astype(np.float32)
+    b = rng.standard_normal((K_, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    da, db = dev(a), dev(b)
+    at, bt = da.t().contiguous(), db.t().contiguous()          # stored [K, M] / [N, K]
+    outs = [K.gemm(da, db, precision="tf32"), K.gemm(at, db, trans_a=True, precision="tf32"),
+            K.gemm(da, bt, trans_b=True, precision="tf32"), K.gemm(at, bt, trans_a=True, trans_b=True, precision="tf32")]
+    for o in outs:
+        assert rel_err(o.cpu().numpy(), ref) <= TF32_TOL
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    # row strides that are 16-byte multiples (the layout of the feature tables): no copy at all
+    ld_a, ld_b = (K_ + 3) // 4 * 4 + 4, (N + 3) // 4 * 4
+    pa, pb = padded(a, ld_a)[:, :K_], padded(b, ld_b)[:, :N]
+    assert torch.equal(K.gemm(pa, pb, precision="tf32"), outs[0])
+    out = K.gemm(da, db, bias=dev(bias), relu=True, precision="tf32").cpu().numpy()
+    assert rel_err(out, np.maximum(ref + bias, 0)) <= TF32_TOL
+    acc = rng.standard_normal((M, N)).astype(np.float32)
+    o = dev(acc)
+    K.gemm(da, db, out=o, accumulate=True, precision="tf32")
+    assert rel_err(o.cpu().numpy(), acc + ref) <= TF32_TOL
+    # deterministic
+    assert torch.equal(K.gemm(da, db, precision="tf32"), outs[0])
+
+
+def test_layers_run_on_the_tf32_path():
+    import dgll_b200.nn as nn
+    from dgll_b200 import ops
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(300, 64).cuda()
+    x = torch.randn(500, 300, device="cuda", requires_grad=True)
+    ref = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
+    out = ops.linear(x, lin.weight, bias=lin.bias, trans_w=True, precision="tf32")
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= TF32_TOL
+    g = torch.randn_like(out)
+    out.backward(g)
+    gx, gw = torch.autograd.grad(ref, [x, lin.weight], g.double(), allow_unused=True)
+    assert rel_err(x.grad.cpu().numpy(), gx.cpu().numpy()) <= TF32_TOL
+    assert rel_err(lin.weight.grad.cpu().numpy(), gw.cpu().numpy()) <= TF32_TOL
 
 
 # ------------------------------------------------------- tcgen05 GEMM ------

@@ -232,6 +232,68 @@ def test_pooling_matches_scatter_semantics(nn, sorted_batch):
     assert rel_err(xs.grad.cpu(), np.repeat((1.0 / cnt[batch])[:, None], 19, axis=1)) <= OUT_TOL
 
 
+# ------------------------------------------------------ binarized GCN ------
+def test_bin_gcn_conv_forward_exact_and_ste_backward(nn):
+    """BinGCNConv (README.md:11): forward = (mean of the neighbours' sign bits) W + b with integer-exact
+    counts from the popcount kernel; backward = straight-through estimator, checked against torch autograd of the same
+    definition (sign replaced by a clipped identity in the backward pass)."""
+    rng = np.random.default_rng(5)
+    n, Fi, H = 700, 70, 24
+    deg = rng.integers(0, 30, size=n)
+    rp = np.zeros(n + 1, dtype=np.int64)
+    rp[1:] = np.cumsum(deg)
+    col = rng.integers(0, n, size=int(rp[-1])).astype(np.int32)
+    x = (rng.standard_normal((n, Fi)) * 1.5).astype(np.float32)
+    from dgll_b200 import ops
+    g = ops.CsrGraph(cu(rp, torch.int64), cu(col, torch.int32))
+    layer = nn.BinGCNConv(Fi, H).cuda()
+    tx = cu(x).requires_grad_(True)
+    out = layer(tx, g)
+    # reference: dense restatement in fp64 with a straight-through sign
+    A = np.zeros((n, n))
+    np.add.at(A, (np.repeat(np.arange(n), deg), col), 1.0)
+    Am = torch.from_numpy(A / np.maximum(deg, 1)[:, None])
+    rx = torch.from_numpy(x).double().requires_grad_(True)
+
+    class SignSTE(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, v):
+            ctx.save_for_backward(v)
+            return torch.where(v >= 0, torch.ones_like(v), -torch.ones_like(v))
+
+        @staticmethod
+        def backward(ctx, gr):
+            (v,) = ctx.saved_tensors
+            return gr * (v.abs() <= 1.0)
+
+    w, b = layer.weight.detach().double().cpu().requires_grad_(True), layer.bias.detach().double().cpu().requires_grad_(True)
+    ref = (Am @ SignSTE.apply(rx)) @ w + b
+    assert rel_err(out.detach().cpu(), ref.detach()) <= OUT_TOL
+    gout = torch.from_numpy(rng.standard_normal((n, H)).astype(np.float32))
+    out.backward(gout.cuda())
+    ref.backward(gout.double())
+    assert rel_err(tx.grad.cpu(), rx.grad) <= GRAD_TOL
+    assert rel_err(layer.weight.grad.cpu(), w.grad) <= GRAD_TOL
+    assert rel_err(layer.bias.grad.cpu(), b.grad) <= GRAD_TOL
+    # the aggregation itself is integer-exact: equal to the fp32 kernel on sign(x)
+    agg = ops.binarized_aggregate(g, x=cu(x), mode="sum")
+    sx = torch.where(cu(x) >= 0, 1.0, -1.0)
+    assert torch.equal(agg, ops.spmm(g, sx, reduce="sum"))
+    # the two-layer model trains (loss goes down on a fixed batch)
+    torch.manual_seed(0)
+    model = nn.BinGCN(Fi, 32, 5, 0.0).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=0.02)
+    y = cu(rng.integers(0, 5, size=n), torch.int64)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        loss = torch.nn.functional.nll_loss(model(cu(x), g), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.9 * losses[0]
+
+
 # ----------------------------------------------------------------- SAGE ----
 @pytest.mark.parametrize("aggr,combine", [("mean", "sum"), ("sum", "concat"), ("max", "sum")])
 def test_sage_conv_matches_restated_oracle(nn, aggr, combine):
@@ -479,6 +541,90 @@ def test_graph_cache_server_matches_reference_semantics():
     nf2 = NodeFlow([torch.from_numpy(layers[0])])
     srv2.fetch_data(nf2)
     assert np.array_equal(nf2._node_frames[0]["features"].cpu().numpy(), host["features"][nid_map[layers[0]]])
+
+
+def test_graph_cache_server_pinned_by_the_reference_run():
+    """tests/golden/cache_server.npz = what the reference's own GraphCacheServer produced (storage.py executed in place
+    by oracle/gen_golden_pins.py).  With the reference's cache set, bookkeeping arrays, per-layer frames (bit-exact) and
+    the miss statistics must be identical; auto_cache must pick a set that obeys the same out-degree policy."""
+    from dgll_b200.data import GraphCacheServer, NodeFlow
+    g = golden("cache_server")
+    host = {"features": torch.from_numpy(g["feats"]), "norm": torch.from_numpy(g["norm"])}
+    n = g["nid_map"].size
+    nid_map = torch.from_numpy(g["nid_map"])
+    layers = [torch.from_numpy(g["layer%d" % i]) for i in range(3)]
+    flag = g["part_gpu_flag"].astype(bool)
+    ids = np.nonzero(flag)[0]
+    nids = torch.from_numpy(ids[np.argsort(g["part_localid2cacheid"][ids])])
+    srv = GraphCacheServer(host, n, nid_map, 0)
+    srv.init_field(["features", "norm"])
+    assert srv.total_dim == 14
+    srv.cache_fix_data(nids.cuda(), srv.get_feat_from_server(nids.cuda(), ["features", "norm"]))
+    assert np.array_equal(srv.gpu_flag.cpu().numpy(), flag)
+    assert np.array_equal(srv.localid2cacheid.cpu().numpy()[flag], g["part_localid2cacheid"][flag])
+    for name in host:
+        assert np.array_equal(srv.gpu_fix_cache[name].cpu().numpy(), g["part_cache_" + name])
+    srv.log = True
+    nf = NodeFlow(layers)
+    srv.fetch_data(nf)
+    for i in range(3):
+        for name in host:
+            assert np.array_equal(nf._node_frames[i][name].cpu().numpy(), g["part_frame%d_%s" % (i, name)])
+    assert srv.get_miss_rate() == float(g["part_miss_rate"])
+    # to_gpu=True (storage.py:120-122): rows come back on the device
+    fr = srv.get_feat_from_server(layers[2].cuda(), ["features"], to_gpu=True)
+    assert fr["features"].is_cuda and np.array_equal(fr["features"].cpu().numpy(), g["feats"][g["nid_map"][g["layer2"]]])
+    # the fill policy on its own: `capability` nodes, none with a smaller out-degree than an uncached one
+    srv2 = GraphCacheServer(host, n, nid_map, 0)
+    srv2.auto_cache(torch.from_numpy(g["out_deg"]), ["features", "norm"], capability=150)
+    f2 = srv2.gpu_flag.cpu().numpy()
+    assert f2.sum() == 150 and g["out_deg"][f2].min() >= g["out_deg"][~f2].max()
+    strict = g["out_deg"] > g["out_deg"][flag].min()
+    assert np.array_equal(f2[strict], flag[strict])
+    # fully cached
+    srv3 = GraphCacheServer(host, n, nid_map, 0)
+    srv3.auto_cache(torch.from_numpy(g["out_deg"]), ["features", "norm"], capability=n)
+    assert srv3.full_cached and np.array_equal(srv3.localid2cacheid.cpu().numpy(), g["full_localid2cacheid"])
+    nf3 = NodeFlow(layers)
+    srv3.fetch_data(nf3)
+    for i in range(3):
+        for name in host:
+            assert np.array_equal(nf3._node_frames[i][name].cpu().numpy(), g["full_frame%d_%s" % (i, name)])
+
+
+@pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
+@pytest.mark.parametrize("combine", ["sum", "concat"])
+def test_sage_conv_pinned_by_the_repaired_reference(nn, aggr, combine):
+    """tests/golden/nn_sageconv_fixed.npz: the reference's sageconv.py run with its two documented one-line repairs
+    applied to the AST (oracle/gen_golden_pins.py) — outputs and all four gradients."""
+    g = golden("nn_sageconv_fixed")
+    k = "%s_%s_" % (aggr, combine)
+    layer = nn.sageConv(g["src"].shape[1], g[k + "w_self"].shape[1], aggr_neighbor_method=aggr,
+                        aggr_hid_method=combine).cuda()
+    with torch.no_grad():
+        layer.weight.copy_(cu(g[k + "w_self"]))
+        layer.neighborAgg.weight.copy_(cu(g[k + "w_neigh"]))
+    ts, tn = cu(g["src"]).requires_grad_(True), cu(g["neigh"]).requires_grad_(True)
+    out = layer(ts, tn)
+    assert rel_err(out.detach().cpu(), g[k + "out"]) <= OUT_TOL
+    out.backward(cu(g[k + "g"]))
+    assert rel_err(ts.grad.cpu(), g[k + "d_src"]) <= GRAD_TOL
+    assert rel_err(tn.grad.cpu(), g[k + "d_neigh"]) <= GRAD_TOL
+    assert rel_err(layer.weight.grad.cpu(), g[k + "d_w_self"]) <= GRAD_TOL
+    assert rel_err(layer.neighborAgg.weight.grad.cpu(), g[k + "d_w_neigh"]) <= GRAD_TOL
+
+
+def test_graphsage_model_pinned_by_the_repaired_reference(nn):
+    g = golden("nn_sageconv_fixed")
+    fan = [int(v) for v in g["model_fan"]]
+    model = nn.GraphSage(g["model_hop0"].shape[1], hidden_dim=[g["model_l0_w_self"].shape[1], g["model_l1_w_self"].shape[1]],
+                         num_neighbors_list=fan).cuda()
+    with torch.no_grad():
+        for i, layer in enumerate(model.gcn):
+            layer.weight.copy_(cu(g["model_l%d_w_self" % i]))
+            layer.neighborAgg.weight.copy_(cu(g["model_l%d_w_neigh" % i]))
+    out = model([cu(g["model_hop%d" % i]) for i in range(3)])
+    assert rel_err(out.detach().cpu(), g["model_out"]) <= OUT_TOL
 
 
 # ------------------------------------------------------- normalisation -----

@@ -4,6 +4,7 @@ import json
 import random
 
 import numpy as np
+import pytest
 import torch
 
 import oracle
@@ -183,6 +184,76 @@ def test_cache_server_split_gather():
     assert np.array_equal(out, fr["features"])
     assert miss == cs.miss_num
     assert 0.0 < cs.get_miss_rate() < 1.0
+
+
+def _ref_cache_order(g, tag="part"):
+    """The node ids the reference cached, in its cache order (storage.py:139: localid2cacheid[nids] = arange)."""
+    flag = g[tag + "_gpu_flag"].astype(bool)
+    ids = np.nonzero(flag)[0]
+    return ids[np.argsort(g[tag + "_localid2cacheid"][ids])]
+
+
+def test_cache_server_restatement_pinned_by_the_reference_run():
+    """tests/golden/cache_server.npz holds what the reference's own GraphCacheServer did (oracle/gen_golden_pins.py
+    executes dgll/FeatureCache/storage.py in place): fill policy, bookkeeping arrays, per-layer frames, miss accounting."""
+    g = golden("cache_server")
+    host = {"features": g["feats"], "norm": g["norm"]}
+    n = g["nid_map"].size
+    layers = [g["layer0"], g["layer1"], g["layer2"]]
+    # fill policy (:84-98): exactly `capability` nodes, none with a smaller out-degree than an uncached one
+    flag = g["part_gpu_flag"].astype(bool)
+    assert flag.sum() == g["part_cached_num"] == 150
+    assert g["out_deg"][flag].min() >= g["out_deg"][~flag].max()
+    cs = S.CacheServer(host, n, g["nid_map"])
+    cs.auto_cache(g["out_deg"], 150, ["features", "norm"])
+    strict = g["out_deg"] > g["out_deg"][flag].min()             # ties at the boundary are the sort's free choice
+    assert np.array_equal(cs.gpu_flag[strict], flag[strict]) and cs.gpu_flag.sum() == 150
+    # same cache set and order as the reference -> identical bookkeeping, frames and miss statistics
+    cs = S.CacheServer(host, n, g["nid_map"])
+    nids = _ref_cache_order(g)
+    cs.cache_fix_data(nids, {k: host[k][g["nid_map"][nids]] for k in host})
+    assert np.array_equal(cs.gpu_flag, flag)
+    assert np.array_equal(cs.localid2cacheid[flag], g["part_localid2cacheid"][flag])
+    for name in host:
+        assert np.array_equal(cs.cache[name], g["part_cache_" + name])
+    for i, ids in enumerate(layers):
+        fr = cs.fetch(ids)
+        for name in host:
+            assert np.array_equal(fr[name], g["part_frame%d_%s" % (i, name)])
+    assert cs.try_num == g["part_try_num"] and cs.miss_num == g["part_miss_num"]
+    assert cs.get_miss_rate() == float(g["part_miss_rate"])
+    # fully cached (:80-83, fetch_from_cache :201-210)
+    cf = S.CacheServer(host, n, g["nid_map"])
+    cf.auto_cache(g["out_deg"], n, ["features", "norm"])
+    assert cf.full_cached and np.array_equal(cf.localid2cacheid, g["full_localid2cacheid"])
+    for i, ids in enumerate(layers):
+        fr = cf.fetch(ids)
+        for name in host:
+            assert np.array_equal(fr[name], g["full_frame%d_%s" % (i, name)])
+
+
+@pytest.mark.parametrize("aggr", ["mean", "sum", "max"])
+@pytest.mark.parametrize("combine", ["sum", "concat"])
+def test_sage_conv_restatement_pinned_by_the_repaired_reference(aggr, combine):
+    """tests/golden/nn_sageconv_fixed.npz: the reference's sageconv.py executed with its two documented one-line
+    repairs applied to the AST (oracle/gen_golden_pins.py)."""
+    g = golden("nn_sageconv_fixed")
+    k = "%s_%s_" % (aggr, combine)
+    src = T(g["src"]).requires_grad_(True)
+    neigh = T(g["neigh"]).requires_grad_(True)
+    ws, wn = T(g[k + "w_self"]).requires_grad_(True), T(g[k + "w_neigh"]).requires_grad_(True)
+    out = L.sage_conv(src, neigh, ws, wn, aggr=aggr, combine=combine)
+    assert rel_err(out.detach(), g[k + "out"]) < 1e-6
+    out.backward(T(g[k + "g"]))
+    for t, name in ((src, "d_src"), (neigh, "d_neigh"), (ws, "d_w_self"), (wn, "d_w_neigh")):
+        assert rel_err(t.grad, g[k + name]) < 1e-6, name
+
+
+def test_graphsage_model_restatement_pinned_by_the_repaired_reference():
+    g = golden("nn_sageconv_fixed")
+    layers = [(T(g["model_l%d_w_self" % i]), T(g["model_l%d_w_neigh" % i])) for i in range(2)]
+    out = L.graphsage_model([T(g["model_hop%d" % i]) for i in range(3)], layers, list(g["model_fan"]))
+    assert rel_err(out, g["model_out"]) < 1e-6
 
 
 def test_fused_kernel_restatement_matches_dense():

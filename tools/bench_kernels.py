@@ -136,25 +136,47 @@ def main():
         except Exception:
             tf = 1590.0
         g = torch.Generator(device=dev).manual_seed(6)
-        for (M, Kd, Nd) in ((160000, 602, 256), (9539, 1204, 256), (2449029, 100, 256), (8192, 8192, 8192)):
-            a = torch.randn((M, Kd), device=dev, generator=g)
-            b = torch.randn((Kd, Nd), device=dev, generator=g)
+        hbm = peak()
+        for (M, Kd, Nd) in ((160000, 602, 256), (11264, 602, 256), (11264, 128, 256), (11264, 256, 172),
+                            (2449029, 100, 256), (8192, 8192, 8192)):
+            ld = (Kd + 3) // 4 * 4                                     # 16-byte rows, as the feature tables are laid out
+            a = torch.randn((M, ld), device=dev, generator=g)[:, :Kd]
+            w = torch.randn((Nd, ld), device=dev, generator=g)[:, :Kd]  # nn.Linear layout [out, in]: K-major for x @ W^T
+            go = torch.randn((M, Nd), device=dev, generator=g)
             out = torch.empty((M, Nd), device=dev)
             flop = 2.0 * M * Kd * Nd
             io_bytes = M * Kd * 4 + Kd * Nd * 4 + M * Nd * 4
-            for prec in ("bf16", "fp32"):
+
+            def rep(name, ms, extra=None):
+                d = {"kernel": name, "shape": "%dx%dx%d" % (M, Kd, Nd), "ms": round(ms, 4), "TFLOPs": round(flop / ms / 1e9, 1),
+                     "frac_of_measured_bf16_peak": round(flop / ms / 1e9 / tf, 3), "io_GBps": round(io_bytes / ms / 1e6, 1),
+                     "io_frac_of_measured_hbm": round(io_bytes / ms / 1e6 / hbm, 3)}
+                d.update(extra or {})
+                print(json.dumps(d), flush=True)
+
+            for prec in ("tf32", "bf16", "fp32"):
                 if prec == "fp32" and M * Kd * Nd > 4e11:
                     continue
-                ms = timeit(lambda: K.gemm(a, b, out=out, precision=prec), args.iters)
-                print(json.dumps({"kernel": "gemm[%s]" % ("tcgen05 bf16" if prec == "bf16" else "simt fp32"),
-                                  "shape": "%dx%dx%d" % (M, Kd, Nd), "ms": round(ms, 4),
-                                  "TFLOPs": round(flop / ms / 1e9, 1), "frac_of_measured_bf16_peak": round(flop / ms / 1e9 / tf, 3),
-                                  "io_GBps": round(io_bytes / ms / 1e6, 1)}), flush=True)
-            ab, bb = a.to(torch.bfloat16), b.to(torch.bfloat16)
-            ms = timeit(lambda: torch.matmul(ab, bb), args.iters)
-            print(json.dumps({"kernel": "torch.matmul bf16 (cuBLAS comparator, operands pre-converted)",
-                              "shape": "%dx%dx%d" % (M, Kd, Nd), "ms": round(ms, 4), "TFLOPs": round(flop / ms / 1e9, 1)}), flush=True)
-            del a, b, out, ab, bb
+                ms = timeit(lambda: K.gemm(a, w, out=out, trans_b=True, precision=prec), args.iters)
+                rep("gemm fwd x@W^T [%s]" % {"tf32": "tcgen05 tf32, TMA on fp32", "bf16": "tcgen05 bf16 + pack", "fp32": "simt fp32"}[prec], ms)
+            if M * Kd * Nd <= 4e11:
+                for prec in ("tf32", "bf16"):
+                    dw = torch.empty((Nd, Kd), device=dev)
+                    ms = timeit(lambda: K.gemm(go, a, trans_a=True, out=dw, precision=prec), args.iters)
+                    rep("gemm dW = G^T X [%s]" % prec, ms)
+                    dx = torch.empty((M, Kd), device=dev)
+                    ms = timeit(lambda: K.gemm(go, w, out=dx, precision=prec), args.iters)
+                    rep("gemm dX = G W [%s]" % prec, ms)
+                    del dw, dx
+            ab, wb = a.to(torch.bfloat16), w.to(torch.bfloat16)
+            ms = timeit(lambda: torch.matmul(ab, wb.t()), args.iters)
+            rep("torch.matmul bf16 (cuBLAS comparator, operands pre-converted, bf16 out)", ms)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            ac, wc = a.contiguous(), w.contiguous()
+            ms = timeit(lambda: torch.matmul(ac, wc.t(), out=out), args.iters)
+            rep("torch.matmul fp32 operands, TF32 allowed (cuBLAS comparator, same I/O as ours)", ms)
+            torch.backends.cuda.matmul.allow_tf32 = False
+            del a, w, go, out, ab, wb, ac, wc
 
     if "gat" in which:
         Np, E, Fp, _ = G.SHAPES["products"]
