@@ -193,35 +193,53 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int q = warp - 4;
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
-        const long long row = static_cast<long long>(m0) + q * 32 + lane;
-        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
-                            (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+        // Every TMA load of this CTA has landed and been consumed (tmem_full_bar follows the last MMA), so the pipeline
+        // stages are free: each epilogue warp stages its 32 x 32 chunk there to turn "one thread = one row" (TMEM lane
+        // layout: 32 rows x 16 B per store instruction) into coalesced stores (4 rows x 128 B per instruction).
+        constexpr int kLdT = 36;                                   // floats per staged row: 16-byte aligned, conflict-light
+        float* tile = reinterpret_cast<float*>(smem) + q * (32 * kLdT);
+        const long long row0 = static_cast<long long>(m0) + q * 32;
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-            if (n0 + c * 32 >= N) break;
+            const int cbase = n0 + c * 32;
+            if (cbase >= N) break;
             uint32_t r[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
-            if (row < M) {
-                float* crow = C + row * ldc;
-                const int cbase = n0 + c * 32;
-                if (vec_ok && cbase + 32 <= N) {
+            if (vec_ok && cbase + 32 <= N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(tile + lane * kLdT + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const int c4 = (lane & 7) * 4;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) {
+                    b4.x = __ldg(bias + cbase + c4); b4.y = __ldg(bias + cbase + c4 + 1);
+                    b4.z = __ldg(bias + cbase + c4 + 2); b4.w = __ldg(bias + cbase + c4 + 3);
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + (lane >> 3);
+                    const long long grow = row0 + rr;
+                    if (grow < M) {
+                        float4 v = *reinterpret_cast<const float4*>(tile + rr * kLdT + c4);
+                        float* dst = C + grow * ldc + cbase + c4;
                         if (accumulate) {
-                            const float4 o = *reinterpret_cast<const float4*>(crow + cbase + j);
+                            const float4 o = *reinterpret_cast<const float4*>(dst);
                             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
                         }
-                        if (bias) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cbase + j));
-                            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                        }
-                        v.x = epi_fn(v.x, epi); v.y = epi_fn(v.y, epi);
-                        v.z = epi_fn(v.z, epi); v.w = epi_fn(v.w, epi);
-                        *reinterpret_cast<float4*>(crow + cbase + j) = v;
+                        v.x = epi_fn(v.x + b4.x, epi); v.y = epi_fn(v.y + b4.y, epi);
+                        v.z = epi_fn(v.z + b4.z, epi); v.w = epi_fn(v.w + b4.w, epi);
+                        *reinterpret_cast<float4*>(dst) = v;
                     }
-                } else {
+                }
+                __syncwarp();
+            } else {
+                const long long row = row0 + lane;
+                if (row < M) {
+                    float* crow = C + row * ldc;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = cbase + j;

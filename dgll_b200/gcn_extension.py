@@ -75,38 +75,35 @@ class GCNFusedFunction(torch.autograd.Function):
 
 
 class GCNLayer(torch.nn.Module):
-    """train_gcn.py:24-41: W ~ N(0,1)/sqrt(actual_F), shape [F_padded, H], created on the device."""
+    """train_gcn.py:24-41, same positional arguments and attribute names: ``GCNLayer(in_features_padded,
+    actual_in_features, out_features)``; ``W`` ~ N(0,1)/sqrt(actual_in_features), shape [in_features_padded,
+    out_features], created on the device; ``actual_F`` = the number of real input columns."""
 
-    def __init__(self, in_features, out_features, padded_in_features, device="cuda"):
+    def __init__(self, in_features_padded, actual_in_features, out_features):
         super().__init__()
-        self.in_features = in_features
-        self.padded_in_features = padded_in_features
-        self.W = torch.nn.Parameter(torch.randn(padded_in_features, out_features, device=device)
-                                    * (1.0 / math.sqrt(in_features)))
+        scale = 1.0 / math.sqrt(actual_in_features)
+        self.W = torch.nn.Parameter(torch.randn(in_features_padded, out_features, dtype=torch.float32, device="cuda") * scale)
+        self.actual_F = actual_in_features
 
     def forward(self, row_ptr, col_idx, values, X, num_neighbors):
-        return GCNFusedFunction.apply(row_ptr, col_idx, values, X, self.W, num_neighbors, self.in_features)
+        return GCNFusedFunction.apply(row_ptr, col_idx, values, X, self.W, num_neighbors, self.actual_F)
 
 
 class GCN(torch.nn.Module):
-    """train_gcn.py:43-57: two fused layers; the input is zero-padded to a multiple of 4 columns once."""
+    """train_gcn.py:43-57, same constructor (``GCN(input_dim, hidden_dim, output_dim)``) and parameter shapes:
+    ``layer1.W`` [pad4(input_dim), hidden_dim], ``layer2.W`` [hidden_dim, output_dim] — the hidden width is NOT padded
+    (the kernels fall back to scalar loads when a row is not a 16-byte multiple), so reference state dicts load."""
 
-    def __init__(self, in_features, hidden, out_features, device="cuda"):
+    def __init__(self, input_dim, hidden_dim, output_dim):
         super().__init__()
-        pad = lambda f: (f + 3) // 4 * 4
-        self.in_features, self.pad_in = in_features, pad(in_features)
-        self.hidden, self.pad_hidden = hidden, pad(hidden)
-        self.layer1 = GCNLayer(in_features, hidden, self.pad_in, device)
-        self.layer2 = GCNLayer(hidden, out_features, self.pad_hidden, device)
+        self.input_dim_padded = ((input_dim + 3) // 4) * 4
+        self.layer1 = GCNLayer(self.input_dim_padded, input_dim, hidden_dim)
+        self.layer2 = GCNLayer(hidden_dim, hidden_dim, output_dim)
 
     def forward(self, row_ptr, col_idx, values, X, num_neighbors):
-        if X.size(1) != self.pad_in:
-            Xp = X.new_zeros((X.size(0), self.pad_in))
-            Xp[:, :X.size(1)] = X
-            X = Xp
-        h = self.layer1(row_ptr, col_idx, values, X, num_neighbors)
-        if h.size(1) != self.pad_hidden:
-            hp = h.new_zeros((h.size(0), self.pad_hidden))
-            hp[:, :h.size(1)] = h
-            h = hp
-        return self.layer2(row_ptr, col_idx, values, h, num_neighbors)
+        if X.size(1) != self.input_dim_padded:
+            X_padded = torch.zeros(X.size(0), self.input_dim_padded, device=X.device, dtype=torch.float32)
+            X_padded[:, :X.size(1)] = X
+            X = X_padded
+        h1 = self.layer1(row_ptr, col_idx, values, X, num_neighbors)
+        return self.layer2(row_ptr, col_idx, values, h1, num_neighbors)

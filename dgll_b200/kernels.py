@@ -188,17 +188,23 @@ def spmm_max_backward(col_idx, argmax, grad_out, n_src):
     return gx
 
 
-def csr_transpose(row_ptr, col_idx, n_cols, values=None, want_perm=False):
-    """CSR of A^T: returns (t_row_ptr, t_col_idx, t_values or None, perm or None)."""
+def csr_transpose(row_ptr, col_idx, n_cols, values=None, want_perm=False, out=None):
+    """CSR of A^T: returns (t_row_ptr, t_col_idx, t_values or None, perm or None).  ``out=(t_row_ptr, t_col_idx, perm)``
+    writes into caller-owned buffers (fixed-capacity pipelines)."""
     _need_cuda(row_ptr, col_idx, values)
     rp, is64 = _rowptr(row_ptr)
     col = _index32(col_idx, "col_idx")
     nnz = col.numel()
     dev = rp.device
-    t_rp = torch.empty(n_cols + 1, dtype=rp.dtype, device=dev)
-    t_col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    if out is not None:
+        t_rp, t_col, perm = out
+        if t_rp.dtype != rp.dtype or t_rp.numel() != n_cols + 1 or t_col.numel() < nnz or (perm is not None and perm.numel() < nnz):
+            raise ValueError("csr_transpose: output buffers do not fit")
+    else:
+        t_rp = torch.empty(n_cols + 1, dtype=rp.dtype, device=dev)
+        t_col = torch.empty(nnz, dtype=torch.int32, device=dev)
+        perm = torch.empty(nnz, dtype=torch.int32, device=dev) if want_perm else None
     t_val = torch.empty(nnz, dtype=torch.float32, device=dev) if values is not None else None
-    perm = torch.empty(nnz, dtype=torch.int32, device=dev) if want_perm else None
     if values is not None:
         values = values.to(torch.float32).contiguous()
     check(lib().dgllb_csr_transpose(_p(rp), is64, _p(col), _p(values), rp.numel() - 1, n_cols, nnz, _p(t_rp),

@@ -113,7 +113,7 @@ class SAGEConv(F.nn.Module):
             F.init.xavier_uniform_(self.fc_self.weight, gain=gain)
         F.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
-    def forward_preaggregated(self, h_neigh_mean, feat_dst):
+    def forward_preaggregated(self, h_neigh_mean, feat_dst, relu=False):
         """The layer applied to an input-feature neighbour MEAN computed upstream (``h_neigh_mean`` [n_dst, in]) and
         the destination rows ``feat_dst`` [n_dst, >= in]: ``W_self x_dst + W_neigh mean_j x_j + b``.  The mean of raw
         input features does not depend on the weights, so a pipelined trainer aggregates mini-batch i+1 — straight from
@@ -121,8 +121,9 @@ class SAGEConv(F.nn.Module):
         ``forward`` up to the order of the linear map and the mean (DGL's ``lin_before_mp`` choice)."""
         if self._aggre_type != "mean":
             raise ValueError("forward_preaggregated: 'mean' aggregator only")
-        rst = ops.linear(feat_dst[:, :self._in_dst_feats], self.fc_self.weight, trans_w=True, bias=self.bias) + \
-            ops.linear(h_neigh_mean, self.fc_neigh.weight, trans_w=True)
+        # two GEMMs into one output; bias (and, when the caller's activation is a ReLU, the ReLU) in the second's epilogue
+        rst = ops.linear2(feat_dst[:, :self._in_dst_feats], self.fc_self.weight, h_neigh_mean, self.fc_neigh.weight,
+                          bias=self.bias, relu=relu, trans_w=True)
         if self.activation is not None:
             rst = self.activation(rst)
         if self.norm is not None:
@@ -147,10 +148,18 @@ class SAGEConv(F.nn.Module):
         lin_before_mp = self._in_src_feats > self._out_feats and feat_table is None
         wn = self.fc_neigh.weight            # [out, in]: used with trans_w=True, no transpose copy
         if self._aggre_type == "mean":
-            if lin_before_mp:
-                h_neigh = ops.spmm(g, ops.linear(feat_src, wn, trans_w=True), reduce="mean")
-            else:
-                h_neigh = ops.linear(ops.spmm(g, feat_src, reduce="mean", F=self._in_src_feats), wn, trans_w=True)
+            x_dst = feat_dst[:, :self._in_dst_feats]
+            if lin_before_mp:    # self term and bias ride in the aggregation's epilogue: no separate add kernels
+                rst = ops.spmm(g, ops.linear(feat_src, wn, trans_w=True), reduce="mean",
+                               addend=ops.linear(x_dst, self.fc_self.weight, trans_w=True), bias=self.bias)
+            else:                # two GEMMs into one output
+                rst = ops.linear2(x_dst, self.fc_self.weight, ops.spmm(g, feat_src, reduce="mean", F=self._in_src_feats),
+                                  wn, bias=self.bias, trans_w=True)
+            if self.activation is not None:
+                rst = self.activation(rst)
+            if self.norm is not None:
+                rst = self.norm(rst)
+            return rst
         elif self._aggre_type == "gcn":
             s = ops.spmm(g, feat_src, reduce="sum", F=self._in_src_feats)
             h_neigh = ops.linear((s + feat_dst[:, :self._in_src_feats]) / (g.degrees()[:, None] + 1), wn, trans_w=True)

@@ -233,7 +233,9 @@ def _fused_attention(x, adj, Ws, a_ls, a_rs, slope, mode, elu, dropout):
     if graph.n_dst != graph.n_src:
         Wh = ops.linear(x, torch.cat(list(Ws), dim=1) if H > 1 else Ws[0])
         Whv = Wh.view(-1, H, D)
-        el = (Whv * torch.stack(list(a_ls))).sum(-1)
+        # a block's destination nodes are its first n_dst source nodes (dst-first compaction, MQGCN.py:45,48): their
+        # "left" scores are the first n_dst rows; autograd zero-pads the gradient of the slice for the other rows
+        el = (Whv * torch.stack(list(a_ls))).sum(-1)[:graph.n_dst]
         er = (Whv * torch.stack(list(a_rs))).sum(-1)
         return ops.gat_aggregate(graph, Wh, el.contiguous(), er.contiguous(), heads=H, slope=slope, mode=mode, elu=elu,
                                  dropout=dropout)

@@ -57,9 +57,14 @@ class GraphSAGE(F.nn.Module):
         upstream (``SAGEConv.forward_preaggregated``); ``blocks[0]`` is then unused and may be ``None``."""
         assert isinstance(blocks, list) and (pre is not None or blocks[0].is_block)
         h = x
+        last = len(self.layers) - 1
         for l, (layer, block) in enumerate(zip(self.layers, blocks)):
             if l == 0 and pre is not None:
-                h = layer.forward_preaggregated(pre[0], pre[1])
+                fuse = l != last and self.activation is torch.relu        # ReLU in the transform's epilogue
+                h = layer.forward_preaggregated(pre[0], pre[1], relu=fuse)
+                if fuse:
+                    h = self.dropout(h)
+                    continue
             elif l == 0 and feat_table is not None:
                 h = layer(block, None, feat_table=feat_table)
             else:

@@ -70,9 +70,17 @@ class CsrGraph:
         self.degrees()
         return self._inv_deg
 
+    @staticmethod
+    def _may_probe():
+        """Plan probing reads one scalar back (a device synchronisation): never while a CUDA graph is being captured —
+        a capture-time graph simply runs without a split plan (fixed-capacity blocks have bounded rows anyway)."""
+        return not torch.cuda.is_current_stream_capturing()
+
     def plan(self):
         """nnz-split schedule when the graph has very long rows (Reddit-shaped skew); None otherwise."""
         if self._plan is False:
+            if not self._may_probe():
+                return None
             self._plan = None
             # only graphs big enough to have such rows are inspected (the check reads one scalar back = one sync
             # per STATIC graph); sampled blocks never pay it
@@ -85,6 +93,8 @@ class CsrGraph:
         """nnz-split into 1,024-edge items: the binarized kernel (integer atomics, exact) and the fused GAT forward
         (partial softmax states merged exactly)."""
         if getattr(self, "_bin_plan", False) is False:
+            if not self._may_probe():
+                return None
             self._bin_plan = None
             if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
                     float(self.degrees().max().item()) > 1024:
@@ -96,6 +106,8 @@ class CsrGraph:
         the products-shaped graph; the forward is best with the 1,024-edge ``bin_plan``: 19.7 ms vs 20.9 ms —
         profiles/r01_kernels.jsonl)."""
         if getattr(self, "_gat_plan", False) is False:
+            if not self._may_probe():
+                return None
             self._gat_plan = None
             if self.n_dst > 0 and self.col is not None and self.col.numel() >= self.PLAN_MIN_EDGES and \
                     float(self.degrees().max().item()) > 256:
@@ -167,7 +179,12 @@ def as_csr(adj, binary=False):
     if not adj.is_cuda:
         raise RuntimeError("dgll_b200: adjacency must live on a CUDA device (there is no CPU fallback)")
     holder = getattr(adj, "_dgllb_csr", None)
-    ver = adj._version if adj.layout == torch.strided else 0
+    if adj.layout == torch.strided:
+        ver = adj._version
+    elif adj.layout == torch.sparse_csr:
+        ver = adj.values()._version
+    else:                                   # in-place edits of a sparse tensor's values bump the values' version
+        ver = adj._values()._version
     if holder is not None and holder.version == (ver, binary):
         return holder.graph
     if adj.layout == torch.strided:
@@ -191,15 +208,16 @@ def as_csr(adj, binary=False):
 # ------------------------------------------------------------------- SpMM ---
 class _SpmmFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, values, bias, graph, reduce, relu, F):
+    def forward(ctx, x, values, bias, graph, reduce, relu, F, addend=None):
         g = graph if values is None else graph.with_values(values)
         want_argmax = reduce == "max" and (x.requires_grad or (values is not None and values.requires_grad))
         plan = graph.plan() if reduce != "max" else None
         res = K.spmm_csr(g.row_ptr, g.col, x, values=g.values, reduce=reduce, n_dst=g.n_dst, bias=bias, relu=relu,
-                         return_argmax=want_argmax, plan=plan, F=F)
+                         return_argmax=want_argmax, plan=plan, F=F, addend=addend)
         out, argmax = res if want_argmax else (res, None)
         ctx.graph, ctx.reduce, ctx.relu = graph, reduce, relu
-        ctx.has_values, ctx.has_bias = values is not None, bias is not None
+        ctx.has_values, ctx.has_bias, ctx.has_addend = values is not None, bias is not None, addend is not None
+        ctx.bias_ref = bias
         ctx.save_for_backward(x, values, out if relu else None, argmax)
         return out
 
@@ -211,8 +229,9 @@ class _SpmmFn(torch.autograd.Function):
         if ctx.relu:
             g = g * (out > 0)
         gx = gv = gb = None
+        ga = g if (ctx.has_addend and ctx.needs_input_grad[7]) else None   # d out / d addend = identity (after the ReLU mask)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)
+            gb = _bias_grad(g, ctx)
         if ctx.reduce == "max":
             if ctx.needs_input_grad[0]:
                 if ctx.has_values:
@@ -220,7 +239,7 @@ class _SpmmFn(torch.autograd.Function):
                 gx = K.spmm_max_backward(graph.col, argmax, g, x.size(0))
                 if gx.size(1) != x.size(1):
                     gx = torch.nn.functional.pad(gx, (0, x.size(1) - gx.size(1)))
-            return gx, None, gb, None, None, None, None
+            return gx, None, gb, None, None, None, None, ga
         if ctx.reduce == "mean":
             g = g * graph.inv_degrees()[:, None]
         if ctx.needs_input_grad[0]:
@@ -239,25 +258,100 @@ class _SpmmFn(torch.autograd.Function):
         if ctx.has_values and ctx.needs_input_grad[1]:
             # d values[e] = <g[row(e)], x[col[e]]>  — the SDDMM SpecialSpmmFunction.backward computes densely (gatconv.py:76-78)
             gv = K.sddmm_csr(graph.row_ptr, graph.col, g, x[:, :g.size(1)].float())
-        return gx, gv, gb, None, None, None, None
+        return gx, gv, gb, None, None, None, None, ga
 
 
-def spmm(adj, x, values=None, reduce="sum", bias=None, relu=False, F=None):
-    """Neighbourhood aggregation with autograd.  ``values`` overrides the graph's edge values (and may require grad)."""
+def spmm(adj, x, values=None, reduce="sum", bias=None, relu=False, F=None, addend=None):
+    """Neighbourhood aggregation with autograd: ``epi(reduce_e(values[e] * x[col[e]]) + addend + bias)``.  ``values``
+    overrides the graph's edge values (and may require grad); ``addend`` [n_dst, F] is added in the kernel's epilogue
+    (the self term of a SAGE layer) and receives the output gradient."""
     graph = as_csr(adj)
     if values is None and graph.values is not None:
         values_arg = None  # static values ride inside the graph object
     else:
         values_arg = values
-    return _SpmmFn.apply(x, values_arg, bias, graph, reduce, relu, F)
+    return _SpmmFn.apply(x, values_arg, bias, graph, reduce, relu, F, addend)
 
 
 # ----------------------------------------------------------------- linear ---
+_DIRECT_GRADS = {"on": False}
+
+
+class direct_weight_grads:
+    """Context manager for trainers that own pre-allocated, pre-zeroed ``.grad`` buffers (``pipelined``): inside it the
+    weight-gradient GEMMs of ``linear`` / ``linear2`` ACCUMULATE straight into ``w.grad`` (split-K reduction included) and
+    return no gradient, and bias gradients are added in place — autograd's per-parameter accumulate kernels disappear."""
+
+    def __enter__(self):
+        self._prev = _DIRECT_GRADS["on"]
+        _DIRECT_GRADS["on"] = True
+
+    def __exit__(self, *a):
+        _DIRECT_GRADS["on"] = self._prev
+
+
+def _weight_grad(a, b, w, precision, trans_a=True):
+    """dW = a^T b as a GEMM; written into ``w.grad`` when direct gradient writes are on (returns None then)."""
+    if _DIRECT_GRADS["on"] and w.grad is not None and w.grad.is_contiguous():
+        K.gemm(a, b, trans_a=trans_a, out=w.grad, accumulate=True, precision=precision)
+        return None
+    return K.gemm(a, b, trans_a=trans_a, precision=precision)
+
+
+def _bias_grad(g, ctx_or_bias):
+    bias = getattr(ctx_or_bias, "bias_ref", None) if not torch.is_tensor(ctx_or_bias) else ctx_or_bias
+    gb = g.sum(0)
+    if _DIRECT_GRADS["on"] and bias is not None and bias.grad is not None:
+        bias.grad.add_(gb)
+        return None
+    return gb
+
+
+class _Linear2Fn(torch.autograd.Function):
+    """``act(x1 @ op(w1) + x2 @ op(w2) + bias)`` — the two transforms of a SAGE layer (self + neighbour) as two GEMMs
+    into ONE output (the second accumulates, bias and ReLU ride in its epilogue); no add / activation kernels."""
+
+    @staticmethod
+    def forward(ctx, x1, w1, x2, w2, bias, relu, precision, trans_w):
+        out = K.gemm(x1, w1, trans_b=trans_w, precision=precision)
+        K.gemm(x2, w2, bias=bias, relu=relu, trans_b=trans_w, out=out, accumulate=True, precision=precision)
+        ctx.relu, ctx.precision, ctx.trans_w = relu, precision, trans_w
+        ctx.bias_ref = bias
+        ctx.save_for_backward(x1, w1, x2, w2, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x1, w1, x2, w2, out = ctx.saved_tensors
+        g = grad.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        p, tw = ctx.precision, ctx.trans_w
+        gx1 = gx2 = gw1 = gw2 = gb = None
+        if ctx.needs_input_grad[0]:
+            gx1 = K.gemm(g, w1, trans_b=not tw, precision=p)
+        if ctx.needs_input_grad[2]:
+            gx2 = K.gemm(g, w2, trans_b=not tw, precision=p)
+        if ctx.needs_input_grad[1]:
+            gw1 = _weight_grad(g, x1, w1, p) if tw else _weight_grad(x1, g, w1, p)
+        if ctx.needs_input_grad[3]:
+            gw2 = _weight_grad(g, x2, w2, p) if tw else _weight_grad(x2, g, w2, p)
+        if ctx.bias_ref is not None and ctx.needs_input_grad[4]:
+            gb = _bias_grad(g, ctx.bias_ref)
+        return gx1, gw1, gx2, gw2, gb, None, None, None
+
+
+def linear2(x1, w1, x2, w2, bias=None, relu=False, precision=None, trans_w=False):
+    """``act(x1 @ w1 + x2 @ w2 + bias)`` on two GEMMs into one output (see ``_Linear2Fn``)."""
+    return _Linear2Fn.apply(x1, w1, x2, w2, bias, relu, precision or _PRECISION["gemm"], trans_w)
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, relu, precision, trans_w):
         out = K.gemm(x, w, bias=bias, relu=relu, trans_b=trans_w, precision=precision)
         ctx.relu, ctx.precision, ctx.trans_w = relu, precision, trans_w
+        ctx.bias_ref = bias
         ctx.save_for_backward(x, w, out if relu else None)
         return out
 
@@ -272,11 +366,11 @@ class _LinearFn(torch.autograd.Function):
             gx = K.gemm(g, w, trans_b=not ctx.trans_w, precision=ctx.precision)      # dX = G W^T
         if ctx.needs_input_grad[1]:
             if ctx.trans_w:
-                gw = K.gemm(g, x, trans_a=True, precision=ctx.precision)              # dW[N,K] = G^T X
+                gw = _weight_grad(g, x, w, ctx.precision)                             # dW[N,K] = G^T X
             else:
-                gw = K.gemm(x, g, trans_a=True, precision=ctx.precision)              # dW[K,N] = X^T G
-        if ctx.needs_input_grad[2]:
-            gb = g.sum(0)
+                gw = _weight_grad(x, g, w, ctx.precision)                             # dW[K,N] = X^T G
+        if ctx.bias_ref is not None and ctx.needs_input_grad[2]:
+            gb = _bias_grad(g, ctx.bias_ref)
         return gx, gw, gb, None, None, None
 
 

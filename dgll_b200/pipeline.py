@@ -20,27 +20,37 @@ import torch
 from . import parallel
 
 
-def sample_generator(gpu_queue, condition, train_dataloader, fetch=None, labels=None, d_stream=None):
-    """Producer (buffer_queues.py:22-70).  ``fetch(input_nodes, mfgs)`` returns the layer-0 input features (or None
-    when the model aggregates straight from the HBM table); ``labels[output_nodes]`` are the targets."""
-    d_stream = d_stream or torch.cuda.Stream()
-    step = -1
-    with torch.cuda.stream(d_stream):
-        for step, (input_nodes, output_nodes, mfgs) in enumerate(train_dataloader):
-            feat = fetch(input_nodes, mfgs) if fetch is not None else None
-            lab = labels[output_nodes] if labels is not None else None
-            ev = torch.cuda.Event()
-            ev.record(d_stream)
-            with condition:
-                while gpu_queue.full():
-                    condition.wait()
-                gpu_queue.put([mfgs, feat, lab, step, ev])
-                condition.notify_all()
+def _put(gpu_queue, condition, item, abort):
+    """Blocking put that gives up when the other side has failed (``abort`` set); returns False in that case."""
     with condition:
         while gpu_queue.full():
-            condition.wait()
-        gpu_queue.put(None)
+            if abort is not None and abort.is_set():
+                return False
+            condition.wait(timeout=0.2)
+        gpu_queue.put(item)
         condition.notify_all()
+    return True
+
+
+def sample_generator(gpu_queue, condition, train_dataloader, fetch=None, labels=None, d_stream=None, abort=None):
+    """Producer (buffer_queues.py:22-70).  ``fetch(input_nodes, mfgs)`` returns the layer-0 input features (or None
+    when the model aggregates straight from the HBM table); ``labels[output_nodes]`` are the targets.  The ``None``
+    sentinel is queued even when the dataloader or ``fetch`` raises, so the consumer never waits for ever; when the
+    consumer has failed (``abort`` set) the producer stops instead of blocking on the full queue."""
+    d_stream = d_stream or torch.cuda.Stream()
+    step = -1
+    try:
+        with torch.cuda.stream(d_stream):
+            for step, (input_nodes, output_nodes, mfgs) in enumerate(train_dataloader):
+                feat = fetch(input_nodes, mfgs) if fetch is not None else None
+                lab = labels[output_nodes] if labels is not None else None
+                ev = torch.cuda.Event()
+                ev.record(d_stream)
+                if not _put(gpu_queue, condition, [mfgs, feat, lab, step, ev], abort):
+                    break
+    finally:
+        if abort is None or not abort.is_set():
+            _put(gpu_queue, condition, None, abort)
     return step + 1
 
 
@@ -70,8 +80,22 @@ def gradient_consumer(opt):
 
 
 def sample_consumer(gpu_queue, condition, opt, model, forward=None, loss_fn=None, group=None, c_stream=None,
-                    g_stream=None, stats=None):
-    """Consumer (buffer_queues.py:74-119).  ``forward(model, mfgs, feat)`` defaults to ``model(mfgs, feat)``."""
+                    g_stream=None, stats=None, abort=None):
+    """Consumer (buffer_queues.py:74-119).  ``forward(model, mfgs, feat)`` defaults to ``model(mfgs, feat)``.  On a
+    failure it sets ``abort`` and drains the queue so a producer blocked on the full queue wakes up."""
+    try:
+        return _consume(gpu_queue, condition, opt, model, forward, loss_fn, group, c_stream, g_stream, stats)
+    except BaseException:
+        if abort is not None:
+            abort.set()
+        with condition:
+            while not gpu_queue.empty():
+                gpu_queue.get()
+            condition.notify_all()
+        raise
+
+
+def _consume(gpu_queue, condition, opt, model, forward, loss_fn, group, c_stream, g_stream, stats):
     c_stream = c_stream or torch.cuda.Stream()
     g_stream = g_stream or torch.cuda.Stream()
     loss_fn = loss_fn or torch.nn.functional.cross_entropy
@@ -129,19 +153,23 @@ def run_epoch(train_dataloader, model, opt, fetch=None, labels=None, forward=Non
     t0 = time.perf_counter()
     dev = torch.cuda.current_device()
 
+    abort = threading.Event()
+
     def _prod():
         torch.cuda.set_device(dev)
-        return sample_generator(gpu_queue, condition, train_dataloader, fetch=fetch, labels=labels)
+        return sample_generator(gpu_queue, condition, train_dataloader, fetch=fetch, labels=labels, abort=abort)
 
     def _cons():
         torch.cuda.set_device(dev)
         return sample_consumer(gpu_queue, condition, opt, model, forward=forward, loss_fn=loss_fn, group=group,
-                               stats=stats)
+                               stats=stats, abort=abort)
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=2) as ex:
         fp, fc = ex.submit(_prod), ex.submit(_cons)
-        fp.result()
-        fc.result()
+        concurrent.futures.wait([fp, fc])
+        for f in (fc, fp):               # surface the failure (the consumer's first: it is the one that aborts the other)
+            if f.exception() is not None:
+                raise f.exception()
     torch.cuda.synchronize()
     stats["time_s"] = time.perf_counter() - t0
     return stats

@@ -49,9 +49,16 @@ class _Slot:
         self.cnt1 = torch.zeros(3, dtype=i32, device=dev)
         self.rp0 = torch.zeros(self.cap_d0 + 1, dtype=i32, device=dev)
         self.nbr0 = torch.zeros(self.cap_e0, dtype=i32, device=dev)
-        self.agg0 = torch.zeros((self.cap_d0, n_feat), dtype=torch.float32, device=dev)
+        # rows are 16-byte multiples so that TMA (the TF32 transform) and 128-bit stores can address them in place
+        self.agg0 = torch.zeros((self.cap_d0, (n_feat + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :n_feat]
         self.self0 = torch.zeros((self.cap_d0, ld_self), dtype=self_dtype, device=dev)
         self._shape = torch.empty(self.cap_d0, dtype=torch.int8, device=dev)   # only its length is used (num_src of block1)
+        # transpose of block1 (for grad_x = A^T g): structure only, so it is built on the produce branch as well
+        self.t_rp1 = torch.zeros(self.cap_d0 + 1, dtype=i32, device=dev)
+        self.t_col1 = torch.zeros(self.cap_e1, dtype=i32, device=dev)
+        self.t_perm1 = torch.zeros(self.cap_e1, dtype=i32, device=dev)
+        self.target = torch.full((B,), -100, dtype=i64, device=dev)            # labels of the seeds, -100 = padding slot
+        self.loss_scale = torch.ones((), dtype=torch.float32, device=dev)      # 1 / (valid seeds * world size)
 
 
 class PipelinedSageTrainer:
@@ -100,7 +107,6 @@ class PipelinedSageTrainer:
         self._arange = torch.arange(self.B, dtype=torch.int64, device=dev)
         self._rng_base = int(rng_seed) * 7919 * 1000003
         self._rng_off = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.loss = torch.zeros((), device=dev)
         self.loss_sum = torch.zeros((), device=dev)
         self.graphs = None
         self._g_train = None
@@ -116,6 +122,7 @@ class PipelinedSageTrainer:
         K.sample_neighbors_cap(self.row_ptr, self.col_idx, s.seeds, self.f1, rng_seed=self._rng_base,
                                rng_offset=self._rng_off, out_row_ptr=s.rp1, out_col=s.nbr1)
         K.build_block_cap(s.seeds, s.rp1, s.nbr1, col_pad=s.cap_d0, src_ids=s.src1, col_local=s.col1, counts=s.cnt1)
+        K.csr_transpose(s.rp1, s.col1, s.cap_d0, want_perm=True, out=(s.t_rp1, s.t_col1, s.t_perm1))
         K.sample_neighbors_cap(self.row_ptr, self.col_idx, s.src1, self.f0, rng_seed=self._rng_base + 1,
                                rng_offset=self._rng_off, out_row_ptr=s.rp0, out_col=s.nbr0)
         if self.sharded is not None:
@@ -126,27 +133,33 @@ class PipelinedSageTrainer:
         else:
             K.spmm_csr(s.rp0, s.nbr0, self.table, reduce="mean", out=s.agg0, F=self.F)
             K.gather_rows(self.table, s.src1.clamp(min=0), out=s.self0)
+        # the loss inputs do not depend on the weights either: the targets and the 1/(valid seeds x world) scale are
+        # produced here, off the training branch
+        valid = s.seeds >= 0
+        lab = self.labels[(s.seeds - self.label_offset).clamp(min=0)]
+        s.target.copy_(torch.where(valid, lab, torch.full_like(lab, -100)))
+        s.loss_scale.copy_(1.0 / (valid.sum().clamp(min=1).to(torch.float32) * self.world))
         self._ctr += 1
         self._rng_off += 1000003
 
     # ------------------------------------------------------------------------------------------ branch A --
     def _train(self, s):
         block1 = G.Block(s.rp1, s.col1, s.col1, s._shape, self.B)
+        g1 = ops.CsrGraph(s.rp1, s.col1, n_src=s.cap_d0)               # with the transpose the produce branch built
+        g1._t, g1._perm = ops.CsrGraph(s.t_rp1, s.t_col1, n_src=self.B), s.t_perm1
+        block1._csr = g1
         self0 = s.self0 if s.self0.dtype == torch.float32 else s.self0.float()
         logits = self.model([None, block1], None, pre=(s.agg0, self0))
-        valid = s.seeds >= 0
-        lab = self.labels[(s.seeds - self.label_offset).clamp(min=0)]
-        target = torch.where(valid, lab, torch.full_like(lab, -100))
-        # mean over the valid seeds; a slot that holds only padding gives 0 (not 0/0), so it can never poison the weights
-        loss = torch.nn.functional.cross_entropy(logits, target, ignore_index=-100, reduction="sum") / \
-            valid.sum().clamp(min=1).to(logits.dtype)
+        # mean over the valid seeds (a slot that holds only padding gives 0, not 0/0), already divided by the world size
+        # so that the SUM all-reduce of the gradients is their average
+        loss = torch.nn.functional.cross_entropy(logits, s.target, ignore_index=-100, reduction="sum") * s.loss_scale
         self._flat.zero_()
-        (loss / self.world if self.world > 1 else loss).backward()    # accumulates into the views of the flat buffer
+        with ops.direct_weight_grads():                                # dW GEMMs accumulate straight into the flat buffer
+            loss.backward()
         if self.world > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
         self.opt.step()
-        self.loss.copy_(loss.detach())
-        self.loss_sum += loss.detach()
+        self.loss_sum.add_(loss.detach(), alpha=float(self.world))     # this rank's mean loss
 
     # ------------------------------------------------------------------------------------------- capture --
     def set_seeds(self, seeds, first_batch=0):

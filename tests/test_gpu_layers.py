@@ -232,6 +232,87 @@ def test_pooling_matches_scatter_semantics(nn, sorted_batch):
     assert rel_err(xs.grad.cpu(), np.repeat((1.0 / cnt[batch])[:, None], 19, axis=1)) <= OUT_TOL
 
 
+def test_as_csr_cache_follows_in_place_edits_of_sparse_values():
+    from dgll_b200 import ops
+    idx = torch.tensor([[0, 1, 2, 2], [1, 0, 0, 1]], device="cuda")
+    adj = torch.sparse_coo_tensor(idx, torch.ones(4, device="cuda"), (3, 3)).coalesce()
+    x = torch.randn(3, 8, device="cuda")
+    a = ops.spmm(adj, x)
+    assert ops.as_csr(adj) is ops.as_csr(adj)                   # converted once per tensor object
+    adj.values().mul_(2.0)                                      # in-place edit: the cached CSR must not be reused
+    b = ops.spmm(adj, x)
+    assert torch.allclose(b, 2 * a)
+
+
+@pytest.mark.timeout(120)
+def test_pipeline_surfaces_thread_failures_instead_of_hanging(nn):
+    """An exception in the producer (dataloader / fetch) or in the consumer (forward) ends run_epoch with that exception:
+    the sentinel is always queued, a failing consumer releases a producer blocked on the full queue."""
+    from dgll_b200 import graphs as G, pipeline
+    N, F = 3000, 16
+    rp, col = G.rmat_csr(N, N * 10, seed=1, device="cuda")
+    table = G.feature_table(N, F, seed=2)
+    labels = torch.randint(0, 3, (N,), device="cuda")
+    model = nn.GraphSAGE(F, 8, 3, 2, torch.relu, 0.0).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+
+    def loader(fail_at=None, n=12):
+        for b in range(n):
+            if fail_at is not None and b == fail_at:
+                raise ValueError("loader failed")
+            s = torch.arange(b * 64, (b + 1) * 64, device="cuda")
+            blocks = G.sample_blocks(rp, col, s, (5, 5), rng_seed=b)
+            yield blocks[0].src_ids, s, blocks
+
+    fwd = lambda m, mfgs, feat: m(mfgs, None, feat_table=table)  # noqa: E731
+    ok = pipeline.run_epoch(loader(), model, opt, labels=labels, forward=fwd, BUFFER_SIZE=2)
+    assert ok["n_batches"] == 12
+    with pytest.raises(ValueError, match="loader failed"):
+        pipeline.run_epoch(loader(fail_at=5), model, opt, labels=labels, forward=fwd, BUFFER_SIZE=2)
+
+    def bad_forward(m, mfgs, feat):
+        raise RuntimeError("forward failed")
+
+    with pytest.raises(RuntimeError, match="forward failed"):
+        pipeline.run_epoch(loader(), model, opt, labels=labels, forward=bad_forward, BUFFER_SIZE=2)
+
+
+def test_gat_layer_trains_on_a_sampled_block(nn):
+    """A GAT layer on a NON-square graph (a sampled block: n_dst < n_src, dst nodes first): forward and all gradients
+    against an fp64 restatement of gatconv.py:30-54 restricted to the block's edges."""
+    from dgll_b200 import ops
+    rng = np.random.default_rng(12)
+    n_src, n_dst, Fi, D = 400, 90, 20, 16
+    deg = rng.integers(1, 12, size=n_dst)
+    rp = np.zeros(n_dst + 1, dtype=np.int64)
+    rp[1:] = np.cumsum(deg)
+    col = rng.integers(0, n_src, size=int(rp[-1])).astype(np.int32)
+    g = ops.CsrGraph(cu(rp, torch.int64), cu(col, torch.int32), n_src=n_src)
+    layer = nn.gatConv(Fi, D, dropout=0.0, alpha=0.2, concat=True).cuda()
+    x = rng.standard_normal((n_src, Fi)).astype(np.float32)
+    tx = cu(x).requires_grad_(True)
+    out = layer(tx, g)
+    assert tuple(out.shape) == (n_dst, D)
+    W = layer.W.detach().double().cpu().requires_grad_(True)
+    a = layer.a.detach().double().cpu().requires_grad_(True)
+    rx = torch.from_numpy(x).double().requires_grad_(True)
+    Wh = rx @ W
+    rows = torch.from_numpy(np.repeat(np.arange(n_dst), deg))
+    cols = torch.from_numpy(col.astype(np.int64))
+    e = torch.nn.functional.leaky_relu((Wh[:n_dst] @ a[:D])[rows, 0] + (Wh @ a[D:])[cols, 0], 0.2)
+    emax = torch.full((n_dst,), -1e30, dtype=torch.float64).scatter_reduce(0, rows, e.detach(), reduce="amax")
+    w = torch.exp(e - emax[rows])
+    alpha = w / torch.zeros(n_dst, dtype=torch.float64).index_add(0, rows, w)[rows]
+    ref = torch.nn.functional.elu(torch.zeros((n_dst, D), dtype=torch.float64).index_add(0, rows, alpha[:, None] * Wh[cols]))
+    assert rel_err(out.detach().cpu(), ref.detach()) <= OUT_TOL
+    gout = torch.from_numpy(rng.standard_normal((n_dst, D)).astype(np.float32))
+    out.backward(gout.cuda())
+    ref.backward(gout.double())
+    assert rel_err(tx.grad.cpu(), rx.grad) <= GRAD_TOL
+    assert rel_err(layer.W.grad.cpu(), W.grad) <= GRAD_TOL
+    assert rel_err(layer.a.grad.cpu(), a.grad) <= GRAD_TOL
+
+
 # ------------------------------------------------------ binarized GCN ------
 def test_bin_gcn_conv_forward_exact_and_ste_backward(nn):
     """BinGCNConv (README.md:11): forward = (mean of the neighbours' sign bits) W + b with integer-exact
@@ -413,7 +494,7 @@ def test_gcn_extension_drop_in(nn):
     h = model(*args)
     ref1 = L.fused_gcn_layer(torch.from_numpy(X[:, :F]).double(), torch.from_numpy(a_hat),
                              model.layer1.W.detach().double().cpu()[:F])
-    ref2 = L.fused_gcn_layer(ref1, torch.from_numpy(a_hat), model.layer2.W.detach().double().cpu()[:Hd])
+    ref2 = L.fused_gcn_layer(ref1, torch.from_numpy(a_hat), model.layer2.W.detach().double().cpu())
     assert rel_err(h.detach().cpu(), ref2) <= OUT_TOL
     loss = torch.nn.functional.binary_cross_entropy_with_logits(h, torch.ones_like(h))
     loss.backward()
@@ -427,6 +508,33 @@ def test_gcn_extension_drop_in(nn):
     a_, b_ = ext.gcn_fused_backward(gout, args[0], args[1], args[2], args[3], model.layer1.W.detach(), args[4], F)
     c_, d_ = ext.gcn_fused_backward(gout, args[0], args[1], args[2], args[3], model.layer1.W.detach(), args[4], F, H=H)
     assert torch.equal(a_, c_) and torch.equal(b_, d_)
+
+
+def test_gcn_extension_reference_constructors_and_state_dict():
+    """The classes take the reference's positional arguments (train_gcn.py:25,44-47) and carry its parameter shapes, also
+    when the hidden width is not a multiple of 4: a reference-shaped state dict loads and the model runs."""
+    from dgll_b200 import gcn_extension as ext
+    layer = ext.GCNLayer(52, 50, 30)                       # (in_features_padded, actual_in_features, out_features)
+    assert tuple(layer.W.shape) == (52, 30) and layer.actual_F == 50
+    model = ext.GCN(50, 30, 121)                           # hidden 30 is not a multiple of 4
+    assert model.input_dim_padded == 52
+    assert tuple(model.layer1.W.shape) == (52, 30) and tuple(model.layer2.W.shape) == (30, 121)
+    assert model.layer2.actual_F == 30
+    sd = {"layer1.W": torch.randn(52, 30), "layer2.W": torch.randn(30, 121)}
+    model.load_state_dict(sd)
+    rng = np.random.default_rng(3)
+    N = 300
+    a = (rng.random((N, N)) < 0.03)
+    a_hat = L.sym_norm_adjacency(a.astype(np.float64))
+    rows, cols = np.nonzero(a_hat)
+    rp, col, val = oracle.coo_to_csr(rows, cols, N, a_hat[rows, cols])
+    X = rng.standard_normal((N, 50)).astype(np.float32)
+    h = model(cu(rp, torch.int32), cu(col, torch.int32), cu(val), cu(X), cu(np.diff(rp), torch.int32))
+    ref1 = L.fused_gcn_layer(torch.from_numpy(X).double(), torch.from_numpy(a_hat), sd["layer1.W"].double()[:50])
+    ref2 = L.fused_gcn_layer(ref1, torch.from_numpy(a_hat), sd["layer2.W"].double())
+    assert rel_err(h.detach().cpu(), ref2) <= OUT_TOL
+    h.sum().backward()
+    assert torch.isfinite(model.layer2.W.grad).all() and tuple(model.layer2.W.grad.shape) == (30, 121)
 
 
 # ------------------------------------------------------------ data path ----

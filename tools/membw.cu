@@ -52,6 +52,38 @@ __global__ void __launch_bounds__(256) gather_read(const char* __restrict__ tabl
     if (s == 123.456f) *sink = s;
 }
 
+// whole-row variant (what spmm_rows_kernel<float,5,4> does): each warp keeps DEPTH random ROWS in flight, 5 x 512 B each
+// (lane reads 16 B at row*stride + s*512 + lane*16, s = 0..4; the 5th piece is the ragged tail of a 2,408-byte row).
+// skew > 0 draws a share of the rows from a small hot set, which reproduces the L2 hit rate of a sampled mini-batch.
+template <int DEPTH>
+__global__ void __launch_bounds__(64) gather_rows(const char* __restrict__ table, uint32_t n_rows, uint32_t stride,
+                                                  int iters, uint32_t hot_rows, uint32_t hot_per_1024, float* sink) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t state = warp * 2654435761u + 12345u;
+    float s = 0.f;
+    const bool last_on = lane * 16 + 2048 < 2408;
+    for (int it = 0; it < iters; ++it) {
+        float4 v[DEPTH][5];
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+            state = state * 1664525u + 1013904223u;
+            uint32_t row = (uint32_t)(((uint64_t)(state >> 4) * n_rows) >> 28);
+            if (((state >> 3) & 1023u) < hot_per_1024) row = row % hot_rows;
+            const char* p = table + (size_t)row * stride + lane * 16;
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                if (q < 4 || last_on) v[u][q] = ldg_nc(reinterpret_cast<const float4*>(p + q * 512));
+        }
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u)
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                if (q < 4 || last_on) s += v[u][q].x + v[u][q].y + v[u][q].z + v[u][q].w;
+    }
+    if (s == 123.456f) *sink = s;
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int main() {
@@ -89,6 +121,23 @@ int main() {
                             bytes / (time_ms(e0, e1) * 1e-3) / 1e9);             \
         }
         RUN(4) RUN(8) RUN(16)
+    }
+    // whole 2,408-byte rows, DEPTH rows in flight per warp, 64-thread blocks (the launch shape of spmm_rows_kernel)
+    for (int hot = 0; hot <= 400; hot += 400) {
+        for (int warps_per_sm = 16; warps_per_sm <= 32; warps_per_sm *= 2) {
+            const int blocks = sms * warps_per_sm / 2 * 4;   // 4 waves
+            const int it4 = 16;
+            const double bytes = (double)blocks * 2 * it4 * 4 * 2408.0;
+#define RUNR(D)                                                                                              \
+            for (int rep = 0; rep < 2; ++rep) {                                                                 \
+                cudaEventRecord(e0);                                                                            \
+                gather_rows<D><<<blocks, 64>>>((const char*)a, n_rows, stride, it4 * 4 / D, 20000, hot, sink);   \
+                cudaEventRecord(e1); cudaEventSynchronize(e1);                                                  \
+                if (rep) printf("gather_rows_2408B depth=%d warps/SM=%-2d hot=%d/1024  %8.1f GB/s\n", D, warps_per_sm, hot, \
+                                bytes / (time_ms(e0, e1) * 1e-3) / 1e9);                                       \
+            }
+            RUNR(2) RUNR(4)
+        }
     }
     // uniform random gather over a table that fits L2 (60 MB): the fabric ceiling for this access shape
     for (int rep = 0; rep < 2; ++rep) {
