@@ -31,6 +31,7 @@ enum Opt {
     OPT_SPMM_KERNEL = 0,   // 0 auto, 1 rowsplit, 2 stream, 3 wholerow
     OPT_SPMM_TB,           // rowsplit kernel block size
     OPT_ROWS_TB, OPT_ROWS_NS, OPT_ROWS_D,   // whole-row kernel: block size, slabs per warp, window depth
+    OPT_ROWS_STREAM,       // whole-row kernel across rows: 0 auto, 1 off, n >= 2 = n rows per warp
     OPT_GAT_KERNEL,        // 0 auto, 1 generic (lane-group), 2 whole-row
     OPT_GAT_ROW_WARPS, OPT_GAT_BWD_TB,
     OPT_BIN_TB,

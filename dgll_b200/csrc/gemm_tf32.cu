@@ -358,6 +358,10 @@ int gemm_tf32(const float* A, long long lda, int transA, const float* B, long lo
     }
     DevInfo di;
     { int rc_ = get_devinfo(&di); if (rc_ != DGLLB_OK) return rc_; }
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context bound to the calling thread, which a fresh
+    // thread (the autograd engine's backward thread) only gets from a context-requiring runtime call — this query is
+    // one, costs nothing and is legal during stream capture
+    { cudaStreamCaptureStatus cs_; DGLLB_CUDA_TRY(cudaStreamIsCapturing(st, &cs_)); }
     // operands TMA cannot address are copied into an aligned workspace first (stored shape: rows x cols)
     const long long a_rows = transA ? K : M, a_cols = transA ? M : K;
     const long long b_rows = transB ? N : K, b_cols = transB ? K : N;

@@ -66,6 +66,7 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"rows_tb", "DGLLB_ROWS_TB", nullptr},
     {"rows_ns", "DGLLB_ROWS_NS", nullptr},
     {"rows_d", "DGLLB_ROWS_D", nullptr},
+    {"rows_stream", "DGLLB_ROWS_STREAM", nullptr},
     {"gat_kernel", "DGLLB_GAT_KERNEL", kGatWords},
     {"gat_row_warps", "DGLLB_GAT_ROW_WARPS", nullptr},
     {"gat_bwd_tb", "DGLLB_GAT_BWD_TB", nullptr},

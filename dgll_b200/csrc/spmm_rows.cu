@@ -197,12 +197,213 @@ spmm_rows_kernel(const RowsParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ streaming variant --
+// The kernel above pays, PER ROW, a chain of dependent round trips before its window is full (row_ptr -> col -> first
+// source rows) and drains the window at the row's end; ncu on the headline block (profiles/r02_spmm_headline.txt):
+// 16 resident warps/SM (128 registers), warps active 22 %, DRAM 51 %, every top stall on the first use of a window slot.
+// A dependency-free gather of the same shape (tools/membw: gather_rows_2408B, depth 4, 16 warps/SM, 40 % of the rows
+// hot in L2) reaches 9.4 TB/s against this kernel's 6.8 — the difference is that per-row start-up and drain.
+// Here a warp owns R CONSECUTIVE rows and streams their concatenated edge list: row ends are fetched once (one
+// coalesced load, broadcast by shuffle), column ids 32 at a time one chunk ahead, and the window of D source rows
+// keeps rolling ACROSS row boundaries — a finished row is scaled and stored while the next row's loads are already
+// in flight.  R is chosen so that the grid is about one wave of resident warps.  Plain epilogue only (sum / mean):
+// anything else takes the per-row kernel.  Every row is owned by one warp: no atomics, deterministic, CSR edge order.
+template <typename XT, int NS, int D, bool HAS_VALS, bool SHARDED>
+__global__ void __launch_bounds__(64)      // no register cap: at <= 128 registers the F=602 window spills and loses (0.099 vs 0.087 ms)
+spmm_rows_stream_kernel(const RowsParams p, const int R) {
+    static_assert(32 % D == 0, "window depth must divide the 32-edge chunk");
+    typedef RowsVec<XT> V;
+    constexpr int A = V::A;
+    constexpr int W = 32 * A;
+    const int lane = threadIdx.x & 31;
+    const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long chunk = wid / p.n_pass;
+    const long long r0 = chunk * R;
+    if (r0 >= p.n_dst) return;
+    const long long r1 = min(r0 + R, p.n_dst);
+    const int pass = static_cast<int>(wid - chunk * p.n_pass);
+    const int col0 = pass * NS * W + lane * A;
+    unsigned on = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) on |= (col0 + s * W < p.F) ? (1u << s) : 0u;
+    const long long lane_off = static_cast<long long>(col0) * static_cast<long long>(sizeof(XT));
+
+    // row boundaries of the owned rows, relative to the first edge: lane l holds the END of row r0 + l (R <= 32)
+    long long ebase;
+    int my_re = 0x7fffffff;
+    {
+        const long long ri = min(r0 + lane, r1);   // lanes past the range read row_ptr[r1] (valid), unused
+        long long v0, v1;
+        if (p.rp64) {
+            v0 = reinterpret_cast<const long long*>(p.row_ptr)[r0];
+            v1 = reinterpret_cast<const long long*>(p.row_ptr)[min(ri + 1, r1)];
+        } else {
+            v0 = reinterpret_cast<const int*>(p.row_ptr)[r0];
+            v1 = reinterpret_cast<const int*>(p.row_ptr)[min(ri + 1, r1)];
+        }
+        ebase = v0;
+        if (r0 + lane < r1) my_re = static_cast<int>(v1 - v0);
+    }
+    const int n_rows = static_cast<int>(r1 - r0);
+    const int m = __shfl_sync(0xffffffffu, my_re, n_rows - 1);   // edges of the whole range
+
+    const int* __restrict__ cb = p.col + ebase;
+    const float* __restrict__ vb = HAS_VALS ? p.vals + ebase : nullptr;
+    auto resolve = [&](int e) -> unsigned long long {   // byte address of edge e's source row (0 past the range)
+        if (e >= m) return 0ull;
+        const int c = __ldg(cb + e);
+        const char* ptr;
+        if (SHARDED) {
+            const int sh = c / p.rows_per_shard;
+            ptr = p.shard_ptrs[sh] + static_cast<long long>(c - sh * p.rows_per_shard) * p.stride_bytes;
+        } else {
+            ptr = p.X + static_cast<long long>(c) * p.stride_bytes;
+        }
+        return reinterpret_cast<unsigned long long>(ptr);
+    };
+    unsigned long long my_a = resolve(lane), my_an = resolve(32 + lane);
+    float my_w = 1.f, my_wn = 1.f;
+    if (HAS_VALS) {
+        my_w = lane < m ? __ldg(vb + lane) : 0.f;
+        my_wn = 32 + lane < m ? __ldg(vb + 32 + lane) : 0.f;
+    }
+
+    int row = 0;                                                  // index inside the owned range
+    int rstart = 0, rend = __shfl_sync(0xffffffffu, my_re, 0);
+
+    typename V::raw_t raw[D][NS];
+    float w[D];
+#pragma unroll
+    for (int u = 0; u < D; ++u) {
+        const char* src = reinterpret_cast<const char*>(__shfl_sync(0xffffffffu, my_a, u)) + lane_off;
+        if (HAS_VALS) w[u] = __shfl_sync(0xffffffffu, my_w, u);
+        if (u < m) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (on & (1u << s)) raw[u][s] = V::load(src + s * (W * static_cast<int>(sizeof(XT))));
+        }
+    }
+    float acc[NS][A];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int a = 0; a < A; ++a) acc[s][a] = 0.f;
+
+    auto flush = [&]() {   // row (r0 + row) is complete: scale, store, move on
+        const int deg = rend - rstart;
+        const float scale = p.mean ? (deg > 0 ? 1.f / static_cast<float>(deg) : 0.f) : 1.f;
+        float* __restrict__ orow = p.out + (r0 + row) * p.ldo + col0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (on & (1u << s)) {
+                const int valid = min(A, p.F - (col0 + s * W));
+                float* __restrict__ o = orow + s * W;
+                if (valid == A && p.out_vec) {
+#pragma unroll
+                    for (int a = 0; a < A; a += 4)
+                        stg_cs_f4(o + a, make_float4(acc[s][a] * scale, acc[s][a + 1] * scale, acc[s][a + 2] * scale,
+                                                     acc[s][a + 3] * scale));
+                } else {
+#pragma unroll
+                    for (int a = 0; a < A; ++a)
+                        if (a < valid) o[a] = acc[s][a] * scale;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < A; ++a) acc[s][a] = 0.f;
+        }
+        rstart = rend;
+        ++row;
+        const int nr = __shfl_sync(0xffffffffu, my_re, row & 31);
+        rend = row < n_rows ? nr : 0x7fffffff;                    // past the range: nothing ends any more
+    };
+
+    for (int jb = 0; jb < m; jb += 32) {
+#pragma unroll 1
+        for (int k = 0; k < 32; k += D) {
+            if (jb + k >= m) break;
+            const bool nxt = k + D >= 32;                         // the refills of this group come from the next chunk
+            const unsigned long long asel = nxt ? my_an : my_a;
+            const float wsel = nxt ? my_wn : my_w;
+#pragma unroll
+            for (int u = 0; u < D; ++u) {
+                const int j = jb + k + u;
+                while (j >= rend) flush();                        // rows that ended before edge j (also empty rows)
+                if (j < m) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        if (on & (1u << s)) {
+                            float v[A];
+                            V::unpack(raw[u][s], v);
+#pragma unroll
+                            for (int a = 0; a < A; ++a)
+                                acc[s][a] = HAS_VALS ? fmaf(w[u], v[a], acc[s][a]) : acc[s][a] + v[a];
+                        }
+                    }
+                }
+                const int srcl = (k + D + u) & 31;
+                const char* src = reinterpret_cast<const char*>(__shfl_sync(0xffffffffu, asel, srcl)) + lane_off;
+                if (HAS_VALS) w[u] = __shfl_sync(0xffffffffu, wsel, srcl);
+                if (j + D < m) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        if (on & (1u << s)) raw[u][s] = V::load(src + s * (W * static_cast<int>(sizeof(XT))));
+                }
+            }
+        }
+        my_a = my_an;
+        my_an = resolve(jb + 64 + lane);
+        if (HAS_VALS) {
+            my_w = my_wn;
+            my_wn = jb + 64 + lane < m ? __ldg(vb + jb + 64 + lane) : 0.f;
+        }
+    }
+    while (row < n_rows) flush();
+}
+
 // block size (threads), slabs per warp and window depth can be pinned for A/B runs (options rows_tb/rows_ns/rows_d)
 struct RowsTuning { int tb, ns, depth; };
 static RowsTuning rows_tuning() { return {opt_get(OPT_ROWS_TB), opt_get(OPT_ROWS_NS), opt_get(OPT_ROWS_D)}; }
 
+// rows per warp of the streaming kernel: 2..16, aiming at about two waves of resident warps (measured on the headline
+// block, profiles/r02_spmm_rows_sweep.md: 2-3 rows per warp 87-88 us, per-row kernel 90.8 us, 4-5 rows per warp — about
+// ONE wave — 102-122 us: every warp then walks through its start-up chain at the same moment)
+static int stream_rows_per_warp(long long n_dst, int n_pass, int sm_count, int resident) {
+    const int forced = opt_get(OPT_ROWS_STREAM);
+    if (forced > 1) return forced > 32 ? 32 : forced;
+    const double slots = static_cast<double>(sm_count) * resident * 2.0;
+    long long r = static_cast<long long>(static_cast<double>(n_dst) * n_pass / slots);
+    if (r < 2) r = 2;
+    if (r > 16) r = 16;
+    return static_cast<int>(r);
+}
+
 template <typename XT, int NS, int D, bool HAS_VALS, bool SHARDED>
 static int rows_launch(const RowsParams& p, int tb, cudaStream_t st) {
+    constexpr int DS = (D >= 8) ? 8 : (D >= 3 ? 4 : 2);                       // streaming depth must divide 32
+    const bool plain = !p.row_scale && !p.addend && !p.bias && !p.epi;
+    // bf16 rows: the streaming variant measured slower than the per-row kernel (70.5 vs 78.3 us) — fp32 only
+    if (plain && opt_get(OPT_ROWS_STREAM) != 1 && (sizeof(XT) == 4 || opt_get(OPT_ROWS_STREAM) > 1) && p.n_dst >= 256) {
+        DevInfo di;
+        int rc = get_devinfo(&di);
+        if (rc != DGLLB_OK) return rc;
+        static const int resident = [] {   // resident warps per SM of this instantiation (64-thread blocks)
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmm_rows_stream_kernel<XT, NS, DS, HAS_VALS, SHARDED>, 64, 0) != cudaSuccess || nb <= 0)
+                nb = 8;
+            return nb * 2;
+        }();
+        const int R = stream_rows_per_warp(p.n_dst, p.n_pass, di.sm_count, resident);
+        if (R >= 2) {
+            const long long warps = (p.n_dst + R - 1) / R * p.n_pass;
+            const long long blocks = (warps + 1) / 2;
+            DGLLB_REQUIRE(blocks < (1ll << 31), "spmm_rows: grid too large (%lld blocks)", blocks);
+            spmm_rows_stream_kernel<XT, NS, DS, HAS_VALS, SHARDED><<<static_cast<unsigned>(blocks), 64, 0, st>>>(p, R);
+            DGLLB_LAUNCH_CHECK();
+            return DGLLB_OK;
+        }
+    }
     const long long warps = p.n_dst * p.n_pass;
     const long long blocks = (warps * 32 + tb - 1) / tb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "spmm_rows: grid too large (%lld blocks)", blocks);

@@ -69,7 +69,7 @@ int64_t dgllb_launch_count(void);
  * environment variable DGLLB_<NAME> (read ONCE per process) and is changed afterwards only here; no launch path calls
  * getenv().  `value` is a decimal integer or one of the option's words; NULL / "" / "auto" = library default.
  *   spmm_kernel  auto | rowsplit | stream | wholerow        gat_kernel  auto | group | row
- *   spmm_tb, rows_tb, rows_ns, rows_d, gat_row_warps, gat_bwd_tb, bin_tb, gemm_kernel   integers (0 = default)
+ *   spmm_tb, rows_tb, rows_ns, rows_d, rows_stream (1 = off, n >= 2 = n rows per warp), gat_row_warps, gat_bwd_tb, bin_tb, gemm_kernel   integers (0 = default)
  *   nvtx         1 = NVTX ranges around the entry points named like the reference's (FeatureCache/storage.py:164-206)
  */
 int dgllb_set_option(const char* name, const char* value);

@@ -616,11 +616,12 @@ def spmm_family(K):
         for k, v in opts.items():
             K.set_option(k, v)
     yield pin
-    for k in ("spmm_kernel", "rows_tb", "rows_ns", "rows_d", "spmm_tb"):
+    for k in ("spmm_kernel", "rows_tb", "rows_ns", "rows_d", "rows_stream", "spmm_tb"):
         K.set_option(k, None)
 
 
-@pytest.mark.parametrize("family", ["rowsplit", "stream", "wholerow", "wholerow:ns2", "wholerow:ns3:d8"])
+@pytest.mark.parametrize("family", ["rowsplit", "stream", "wholerow", "wholerow:ns2", "wholerow:ns3:d8", "wholerow:st1",
+                                    "wholerow:st2", "wholerow:st7", "wholerow:st32", "wholerow:ns1:st3"])
 @pytest.mark.parametrize("F,ld,dt", [(602, 604, "f32"), (256, 256, "f32"), (128, 128, "f32"), (100, 100, "f32"),
                                      (602, 608, "bf16"), (1000, 1000, "f32"), (36, 36, "f32"), (1500, 1504, "bf16")])
 def test_spmm_kernel_families_agree_with_oracle(K, family, F, ld, dt, spmm_family):
@@ -628,7 +629,8 @@ def test_spmm_kernel_families_agree_with_oracle(K, family, F, ld, dt, spmm_famil
     kernel (with its slabs-per-warp / window-depth variants): all must match the oracle on ragged blocks (empty rows,
     short rows, one long row, rows straddling chunk borders)."""
     parts = family.split(":")
-    spmm_family(parts[0], **{("rows_ns" if o.startswith("ns") else "rows_d"): int(o.lstrip("nsd")) for o in parts[1:]})
+    names = {"ns": "rows_ns", "d": "rows_d", "st": "rows_stream"}      # st1 = per-row kernel, st<n> = n rows per warp
+    spmm_family(parts[0], **{names[o.rstrip("0123456789")]: int(o.lstrip("nsdt")) for o in parts[1:]})
     rng = np.random.default_rng(F + len(family))
     n_dst, n_src = 2500, 4000
     rp, col = rand_csr(rng, n_dst, n_src, 37, heavy=[(5, 1500), (2499, 300)], empty_frac=0.15)

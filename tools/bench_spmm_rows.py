@@ -66,21 +66,24 @@ def main():
 
     def run(name, shape, fn, batches, nbytes, opts):
         K.set_option("spmm_kernel", opts.get("family"))
-        for k in ("rows_tb", "rows_ns", "rows_d", "spmm_tb"):
+        for k in ("rows_tb", "rows_ns", "rows_d", "rows_stream", "spmm_tb"):
             K.set_option(k, opts.get(k))
         mean, med = time_batches(fn, batches)
         print(json.dumps({"case": name, "shape": shape, **{k: v for k, v in opts.items() if v is not None},
                           "ms_mean": round(mean, 4), "ms_median": round(med, 4), "alg_MB": round(nbytes / 1e6, 1),
                           "GBps": round(nbytes / mean / 1e6, 1), "frac": round(nbytes / mean / 1e6 / peak(), 3)}),
               flush=True)
-        for k in ("spmm_kernel", "rows_tb", "rows_ns", "rows_d", "spmm_tb"):
+        for k in ("spmm_kernel", "rows_tb", "rows_ns", "rows_d", "rows_stream", "spmm_tb"):
             K.set_option(k, None)
 
-    variants = [dict(family="rowsplit"), dict(family="stream")]
-    for ns, ds in ((5, (3, 4, 5, 6)), (3, (3, 5, 8)), (2, (4, 8, 12)), (1, (4, 8, 16))):
-        for d in ds:
-            for tb in ((64,) if (args.quick or (ns, d) not in ((5, 4), (3, 5))) else (32, 64, 128)):
-                variants.append(dict(family="wholerow", rows_ns=ns, rows_d=d, rows_tb=tb))
+    variants = [dict(family="rowsplit"), dict(family="stream"), dict(family="wholerow", rows_stream=1)]
+    for st in (0, 2, 3, 4, 5, 6, 8):
+        variants.append(dict(family="wholerow", rows_stream=st))
+    for tb in (32, 128):
+        variants.append(dict(family="wholerow", rows_stream=0, rows_tb=tb))
+    variants.append(dict(family="wholerow", rows_stream=0, rows_ns=3))
+    variants.append(dict(family="wholerow", rows_stream=0, rows_d=2))
+    variants.append(dict(family="wholerow", rows_stream=0, rows_d=8))
 
     # ---- headline: block0 of batch 1024, F=602 fp32 (ld 604), output ld 602 and 604 -----------------------------
     table = G.feature_table(N, F, seed=0, device=dev, pad_to=604)
@@ -90,7 +93,7 @@ def main():
         outs = [torch.empty((b0.num_dst, ldo), device=dev)[:, :F] for b0, _ in bl]
         items = list(zip(bl, outs))
         for v in variants:
-            if ldo == 604 and v["family"] == "wholerow" and (v["rows_ns"], v["rows_d"]) not in ((5, 4), (3, 5), (5, 3)):
+            if ldo == 602 and v.get("rows_stream") not in (None, 0, 1):
                 continue
             run("block0 F=602 fp32", "batch=1024 ldo=%d n_dst~%d nnz~%d" % (ldo, bl[0][0].num_dst, bl[0][0].num_edges()),
                 lambda it: K.spmm_csr(it[0][0].row_ptr, it[0][0].col_global, table, reduce="mean", out=it[1], F=F),
@@ -100,8 +103,9 @@ def main():
     nbytes16 = sum(b0.num_edges() * (4 + F * 2) + b0.num_dst * (F * 4 + 4) for b0, _ in bl) / len(bl)
     outs = [torch.empty((b0.num_dst, 604), device=dev)[:, :F] for b0, _ in bl]
     items = list(zip(bl, outs))
-    for v in [dict(family="rowsplit"), dict(family="stream")] + [dict(family="wholerow", rows_ns=ns, rows_d=d)
-                                                                  for ns, d in ((3, 3), (3, 5), (3, 8), (2, 8), (1, 8))]:
+    for v in [dict(family="rowsplit"), dict(family="stream"), dict(family="wholerow", rows_stream=1),
+              dict(family="wholerow", rows_stream=0), dict(family="wholerow", rows_stream=4), dict(family="wholerow", rows_stream=8),
+              dict(family="wholerow", rows_stream=0, rows_d=8), dict(family="wholerow", rows_stream=0, rows_ns=2)]:
         run("block0 F=602 bf16", "batch=1024 ld=%d" % tb16.size(1),
             lambda it: K.spmm_csr(it[0][0].row_ptr, it[0][0].col_global, tb16, reduce="mean", out=it[1], F=F),
             items, nbytes16, v)
@@ -111,8 +115,8 @@ def main():
     outs = [torch.empty((b1.num_dst, 256), device=dev) for _, b1 in bl]
     items = list(zip(bl, hs, outs))
     nb1 = sum(b1.num_edges() * (4 + 256 * 4) + b1.num_dst * (256 * 4 + 4) for _, b1 in bl) / len(bl)
-    for v in [dict(family="rowsplit"), dict(family="wholerow", rows_ns=2, rows_d=8), dict(family="wholerow", rows_ns=2, rows_d=4),
-              dict(family="wholerow", rows_ns=1, rows_d=8)]:
+    for v in [dict(family="rowsplit"), dict(family="wholerow", rows_stream=1), dict(family="wholerow", rows_stream=0),
+              dict(family="wholerow", rows_stream=2)]:
         run("block1 F=256 fp32", "batch=1024 n_dst=1024",
             lambda it: K.spmm_csr(it[0][1].row_ptr, it[0][1].col, it[1], reduce="mean", out=it[2]), items, nb1, v)
     del hs, outs
@@ -122,8 +126,8 @@ def main():
         nb8 = sum(b0.num_edges() * (4 + F * 4) + b0.num_dst * (F * 4 + 4) for b0, _ in bl8) / len(bl8)
         outs = [torch.empty((b0.num_dst, 604), device=dev)[:, :F] for b0, _ in bl8]
         items = list(zip(bl8, outs))
-        for v in [dict(family="rowsplit"), dict(family="stream"), dict(family="wholerow", rows_ns=5, rows_d=4),
-                  dict(family="wholerow", rows_ns=3, rows_d=5)]:
+        for v in [dict(family="rowsplit"), dict(family="stream"), dict(family="wholerow", rows_stream=1),
+                  dict(family="wholerow", rows_stream=0), dict(family="wholerow", rows_stream=16)]:
             run("block0 F=602 fp32 batch 8192", "nnz~%d" % bl8[0][0].num_edges(),
                 lambda it: K.spmm_csr(it[0][0].row_ptr, it[0][0].col_global, table, reduce="mean", out=it[1], F=F),
                 items, nb8, v)
@@ -134,8 +138,8 @@ def main():
     outs = [torch.empty((b0.num_dst, 128), device=dev) for b0, _ in bl]
     items = list(zip(bl, outs))
     nb128 = sum(b0.num_edges() * (4 + 128 * 4) + b0.num_dst * (128 * 4 + 4) for b0, _ in bl) / len(bl)
-    for v in [dict(family="rowsplit"), dict(family="wholerow", rows_ns=1, rows_d=4), dict(family="wholerow", rows_ns=1, rows_d=8),
-              dict(family="wholerow", rows_ns=1, rows_d=16)]:
+    for v in [dict(family="rowsplit"), dict(family="wholerow", rows_stream=1), dict(family="wholerow", rows_stream=0),
+              dict(family="wholerow", rows_stream=2), dict(family="wholerow", rows_stream=4), dict(family="wholerow", rows_stream=0, rows_d=8)]:
         run("block0 F=128 fp32", "batch=1024 (table 119 MB: L2 resident)",
             lambda it: K.spmm_csr(it[0][0].row_ptr, it[0][0].col_global, t128, reduce="mean", out=it[1]), items, nb128, v)
         # the same through the sharded entry point with ONE shard (what the partitioned trainer launches on 1 GPU)
