@@ -381,10 +381,13 @@ def extra_partitioned(args, rank, world, dev, barrier):
         barrier()
         r = tr.epoch(seeds)                                  # the whole epoch, measured (not extrapolated)
         barrier()
+        tr.set_seeds(seeds[:BATCH])
+        tr._prologue.replay()                                # a FULL mini-batch in slot 0 for the traffic statistics
         halo = tr.halo_stats()
         stage = tr.stage_times(seeds[:24 * BATCH], steps=24)
         t = torch.tensor([r["time_s"], stage["produce_ms"], stage["train_ms"], halo["remote_edge_fraction"],
-                          float(halo["remote_bytes_per_step"])], device=dev, dtype=torch.float64)
+                          float(halo["remote_bytes_per_step"]), float(halo["block0_edges"]), float(halo["block0_dst_rows"])],
+                         device=dev, dtype=torch.float64)
         mx = t.clone()
         if world > 1:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -401,7 +404,9 @@ def extra_partitioned(args, rank, world, dev, barrier):
                "stage_ms_alone": {"sample+halo+aggregate (branch B)": round(mx[1].item(), 4),
                                          "fwd+bwd+all-reduce+Adam (branch A)": round(mx[2].item(), 4)},
                "remote_edge_fraction_measured": round(t[3].item(), 4),
-               "nvlink_bytes_in_per_gpu_per_step": int(t[4].item()), "loss": round(r["loss"], 4)}
+               "nvlink_bytes_in_per_gpu_per_step": int(t[4].item()),
+               "block0_edges_per_step": int(t[5].item()), "block0_dst_rows_per_step": int(t[6].item()),
+               "loss": round(r["loss"], 4)}
         for p in model.parameters():
             p.grad = None
         barrier()                                            # no peer may still be reading this rank's shard
@@ -460,6 +465,65 @@ def extra_partitioned(args, rank, world, dev, barrier):
             u_col[o:o + m] = torch.randint(0, N, (m,), device=dev, generator=g, dtype=torch.int32)
         run_peer(table, "peer_fp32_uniform_control_graph", u_rp, u_col)
 
+    def run_cpu_baseline():
+        """the reference CPU aggregation on K = 20 of this run's own mini-batches (device-sampled,
+        copied to the host), source rows taken from a host table slice; epoch figure extrapolated."""
+        import numpy as np
+        import oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        Kb, rows_host = 20, 2_000_000
+        torch.manual_seed(args.seed)
+        m = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
+        o = torch.optim.Adam(m.parameters(), lr=0.003, fused=True, capturable=True)
+        sh = P.PeerShardedTable(N, table) if world == 1 else None
+        if sh is None:
+            return                                           # CPU arm only at N = 1 (the contract's rank-0 rule)
+        tr = PL.PipelinedSageTrainer(m, o, labels, row_ptr, col, F, sharded=sh, batch_size=BATCH, fanouts=FANOUTS,
+                                     precision="tf32", rng_seed=11, label_offset=lo, max_seeds=Kb * BATCH)
+        tr.set_seeds(seeds[:Kb * BATCH])
+        blocks = []
+        for _ in range(Kb):
+            tr._produce(tr.slots[0])
+            sl = tr.slots[0]
+            n0, e0, e1 = int(sl.cnt1[0]), int(sl.rp0[-1]), int(sl.rp1[-1])
+            blocks.append((sl.rp0[:n0 + 1].cpu().numpy().astype(np.int64), (sl.nbr0[:e0].cpu().numpy() % rows_host).astype(np.int32),
+                           sl.rp1.cpu().numpy().astype(np.int64), sl.col1[:e1].cpu().numpy().astype(np.int32)))
+        for p_ in m.parameters():
+            p_.grad = None
+        x = np.random.default_rng(args.seed).standard_normal((rows_host, F), dtype=np.float32)
+        xt = torch.from_numpy(x)
+        h = np.random.default_rng(1).standard_normal((BATCH * (1 + FANOUTS[1]), HIDDEN), dtype=np.float32)
+
+        def step_csr(b):
+            rp0, c0, rp1, c1 = b
+            oracle.spmm_csr(rp0, c0, x, reduce="mean")
+            oracle.spmm_csr(rp1, c1, h, reduce="mean")
+
+        def step_coo(b):
+            rp0, c0, rp1, c1 = b
+            for rp_, c_, src in ((rp0, c0, xt), (rp1, c1, torch.from_numpy(h))):
+                deg = np.diff(rp_)
+                rows_ = torch.from_numpy(np.repeat(np.arange(rp_.size - 1), deg))
+                a = torch.sparse_coo_tensor(torch.stack([rows_, torch.from_numpy(c_).long()]),
+                                            torch.from_numpy(np.repeat(1.0 / np.maximum(deg, 1).astype(np.float32), deg)),
+                                            (rp_.size - 1, src.size(0)))
+                torch.sparse.mm(a, src)
+
+        res = {}
+        for name, fn in (("coo", step_coo), ("csr", step_csr)):
+            fn(blocks[0])
+            t0 = time.perf_counter()
+            for b in blocks:
+                fn(b)
+            res[name] = (time.perf_counter() - t0) / Kb
+        best = min(res, key=res.get)
+        out["cpu_baseline_extrapolated"] = {
+            "kind": "port", "cores": os.cpu_count(), "sample": "K=%d of this run's mini-batches (device-sampled, copied to the "
+            "host), aggregation of both blocks only (no transforms, no backward: a LOWER bound on the CPU step), source rows "
+            "from a %d-row host table slice; torch.sparse.mm COO as gcnconv.py:31 and the OpenMP CSR port" % (Kb, rows_host),
+            "ms_per_step": {k: round(v * 1e3, 3) for k, v in res.items()}, "best": best,
+            "seeds_per_s": round(BATCH / res[best], 1), "epoch_s_extrapolated": round(n_train / BATCH * res[best], 2)}
+
     for tag, fn in (("peer_fp32", lambda: run_peer(table, "peer_fp32")), ("nccl_all_to_all", run_nccl),
                     ("peer_bf16_table", lambda: run_peer(table.to(torch.bfloat16), "peer_bf16_table")),
                     ("peer_fp32_uniform_control_graph", run_uniform_control)):
@@ -468,6 +532,11 @@ def extra_partitioned(args, rank, world, dev, barrier):
         except Exception as ex:
             out["mechanisms"][tag] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
         barrier()
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            run_cpu_baseline()
+        except Exception as ex:
+            out["cpu_baseline_extrapolated"] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
     return out
 
 
@@ -794,7 +863,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(world, n_dst0, nnz0),
-        "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel<float,5,4> (layer-0 mean aggregation, F=602, whole row per warp)",
+        "roofline": {"bound": "hbm", "kernel": "spmm_rows_stream_kernel<float,5,4> (layer-0 mean aggregation, F=602: whole rows per warp, window rolling across rows)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": "%s (ncu --set full)" % traffic_src if traffic_src else None,
                      "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,

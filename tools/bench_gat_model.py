@@ -49,12 +49,60 @@ class GAT3(torch.nn.Module):
         return self.out(self.l1(self.l0(x, adj), adj), adj)
 
 
+def cpu_baseline(adj, x, Np, nnz, slices):
+    """The reference's sparse GAT layer on the host (gatconv.py:111-148: h W, [E, 2D] edge features, exp(-leakyrelu),
+    row sums, weighted sum, ELU; forward + backward through torch autograd, all host threads) for ONE 4-head hidden layer,
+    on the destination rows of a 1/`slices` node range with all their in-edges; the full-graph, three-layer figure is
+    extrapolated (x slices x 3 layers, the 47-class layer counted like a hidden one).  The reference's own backward
+    (SpecialSpmmFunction, :76) is a dense N x N product and cannot run at this size at all."""
+    import os
+    import time
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_dst = Np // slices
+    rp = adj.row_ptr[:n_dst + 1].cpu()
+    e = int(rp[-1])
+    cols = adj.col[:e].long().cpu()
+    rows = torch.repeat_interleave(torch.arange(n_dst), rp[1:] - rp[:-1])
+    src_ids, inv = torch.unique(cols, return_inverse=True)           # the slice's source nodes, compact
+    h = x[src_ids.to(x.device)].cpu()
+    h_dst = x[:n_dst].cpu()
+    heads, D = 4, 64
+    Ws = [torch.randn(h.size(1), D, requires_grad=True) for _ in range(heads)]
+    As = [torch.randn(1, 2 * D, requires_grad=True) for _ in range(heads)]
+
+    def layer():
+        outs = []
+        for W, a in zip(Ws, As):
+            hw_s, hw_d = h @ W, h_dst @ W
+            edge_h = torch.cat((hw_d[rows], hw_s[inv]), dim=1).t()                      # [2D, E] as gatconv.py:121
+            edge_e = torch.exp(-torch.nn.functional.leaky_relu(a.mm(edge_h).squeeze(), 0.2))
+            rowsum = torch.zeros(n_dst, 1).index_add_(0, rows, edge_e[:, None])
+            hp = torch.zeros(n_dst, D).index_add_(0, rows, edge_e[:, None] * hw_s[inv])
+            outs.append(torch.nn.functional.elu(hp / rowsum.clamp(min=1e-30)))
+        return torch.cat(outs, dim=1)
+
+    layer().sum().backward()                                                             # warm-up
+    t0 = time.perf_counter()
+    out = layer()
+    t1 = time.perf_counter()
+    out.sum().backward()
+    t2 = time.perf_counter()
+    fwd, bwd = t1 - t0, t2 - t1
+    return {"kind": "port", "cores": os.cpu_count(), "slice": "1/%d of the destination rows: %d rows, %d edges, %d source rows" % (slices, n_dst, e, src_ids.numel()),
+            "layer_forward_s_on_slice": round(fwd, 3), "layer_backward_s_on_slice": round(bwd, 3),
+            "training_step_s_extrapolated_full_graph_3_layers": round((fwd + bwd) * slices * 3, 1),
+            "forward_s_extrapolated_full_graph_3_layers": round(fwd * slices * 3, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--definition", default="exp_neg", choices=["softmax", "exp_neg"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16", "fp32"])
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cpu-slice", type=int, default=64,
+                    help="time the reference CPU layer (gatconv.py:111-148 restated on an edge list) on a 1/N node-range "
+                         "slice of the destination rows and extrapolate (SURVEY.md §8 d-2); 0 = skip")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     Np, E, Fin, C = G.SHAPES["products"]
@@ -109,7 +157,11 @@ def main():
     def gat_bytes(H, D):
         return nnz * (4 + H * D * 4 + H * 4) + Np * (H * D * 4 + H * 4 + 8)
     fwd_bytes = 2 * gat_bytes(4, 64) + gat_bytes(1, C)
+    cpu = None
+    if args.cpu_slice > 0:
+        cpu = cpu_baseline(adj, x, Np, nnz, args.cpu_slice)
     print(json.dumps({
+        "cpu_baseline_extrapolated": cpu,
         "workload": "GAT 3-layer 4 heads x 64 -> 47, full batch, products-shaped (BASELINE configs[2])",
         "N": Np, "nnz_with_self_loops": nnz, "definition": args.definition, "gemm": args.precision,
         "ms_per_training_step": round(ms_step, 2), "ms_per_forward": round(ms_fwd, 2),
