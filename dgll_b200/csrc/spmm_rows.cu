@@ -428,7 +428,9 @@ static int rows_dispatch(RowsParams& p, cudaStream_t st) {
     p.n_pass = (n_slabs + max_ns - 1) / max_ns;
     const int ns = (n_slabs + p.n_pass - 1) / p.n_pass;
     const int tb = (t.tb == 32 || t.tb == 64 || t.tb == 128) ? t.tb : 64;
-    const int d = t.depth;
+    // rows behind NVLink come back ~3x later than local HBM rows (peer LDG ~2,000 cycles): a deeper window when the rows
+    // are narrow enough for the registers
+    const int d = t.depth ? t.depth : ((SHARDED && ns <= 2) ? 8 : 0);
     switch (ns) {
         case 1: return d == 2 ? rows_launch_v<XT, 1, 2, SHARDED>(p, tb, st)
                      : d == 8 ? rows_launch_v<XT, 1, 8, SHARDED>(p, tb, st)
