@@ -34,6 +34,8 @@ enum Opt {
     OPT_ROWS_STREAM,       // whole-row kernel across rows: 0 auto, 1 off, n >= 2 = n rows per warp
     OPT_GAT_KERNEL,        // 0 auto, 1 generic (lane-group), 2 whole-row
     OPT_GAT_ROW_WARPS, OPT_GAT_BWD_TB,
+    OPT_GAT_BWD_KERNEL,    // 0 auto, 1 two-pass (CSR then CSR^T), 2 fused single pass over CSR^T
+    OPT_GAT_BWD_DEPTH,     // fused backward: gradient rows in flight per lane (4 or 8; 0 = default)
     OPT_BIN_TB,
     OPT_GEMM_KERNEL,       // 0 auto; see gemm_tcgen05.cu
     OPT_NVTX,              // 1 = emit NVTX ranges around the entry points that mirror the reference's ranges

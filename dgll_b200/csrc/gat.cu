@@ -719,6 +719,336 @@ __global__ void gat_bwd_combine_node_kernel(const GatBwdParams p) {
     }
 }
 
+// ------------------------------------------------- fused single-pass backward --
+// The two-pass backward above streams BOTH the source rows Wh_j (pass 1, for dalpha_ij = <g_i, Wh_j>) and the gradient
+// rows g_i (pass 2, for d_Wh_j = sum_i alpha_ij g_i) once per edge, and moves 8 bytes per (edge, head) through a
+// workspace between the passes: products-shaped 55.5 ms against 19.7 ms for the forward.  Both per-edge quantities pair
+// the SAME two rows, so one pass over the transposed CSR does it all: the warp that owns source row j keeps Wh_j and
+// er_j in registers and streams the g_i rows of its edges ONCE — the dot product with the resident Wh_j gives dalpha_ij,
+// the same registers feed d_Wh_j += alpha_ij g_i.  What the pass needs from destination i besides g_i is four scalars
+// per head (el_i, row max, 1/row sum, c_i = <g_i, out_i>), packed by a node-level pre-pass into one 64-byte record that
+// the scoring lane fetches with the column id.  dz_ij leaves as 4 bytes per (edge, head) at the edge's forward position
+// (perm), d_er_j is its sum along the warp's own row, d_el_i its sum along forward row i (a 16-byte-per-edge streaming
+// pass).  No atomics anywhere: every output element has one owner and a fixed summation order.
+// Shapes: the whole-row ones of the forward (16-byte vectors, heads <= 4, 32 <= heads*D <= 512).
+
+// sum four per-lane values over the warp with 6 shuffles: after the call every lane holds the total of value
+// hq = 2*bit4(lane) + bit3(lane) (an 8-lane group per value)
+__device__ __forceinline__ float warp_sum4(float v0, float v1, float v2, float v3, int lane) {
+    const bool up16 = lane & 16;
+    const float s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;          // what the partner keeps
+    float k0 = (up16 ? v2 : v0) + __shfl_xor_sync(0xffffffffu, s0, 16);
+    float k1 = (up16 ? v3 : v1) + __shfl_xor_sync(0xffffffffu, s1, 16);
+    const bool up8 = lane & 8;
+    float r = (up8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// node pre-pass: stats[i][h] = (el_i, row max, 1 / row sum, c_i = <g_i, out_i>) for h < heads, zeros above
+__global__ void __launch_bounds__(128)
+gat_bwd_prep_kernel(const GatBwdParams p, float4* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= p.n_dst) return;
+    const int FD = p.heads * p.D;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = lane * 4; c0 < FD; c0 += 128) {
+        const float4 gv = ldg_nc_f4(p.g + row * p.ldg + c0);
+        const float4 ov = ldg_nc_f4(p.out + row * p.ldo + c0);
+        const float d = gv.x * ov.x + gv.y * ov.y + gv.z * ov.z + gv.w * ov.w;
+        const int h = c0 / p.D;
+        c[0] += h == 0 ? d : 0.f; c[1] += h == 1 ? d : 0.f; c[2] += h == 2 ? d : 0.f; c[3] += h == 3 ? d : 0.f;
+    }
+    const float ci = warp_sum4(c[0], c[1], c[2], c[3], lane);
+    if ((lane & 7) == 0) {
+        const int hq = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hq < p.heads) {
+            const float l = __ldg(p.row_sum + row * p.heads + hq);
+            st = make_float4(__ldg(p.el + row * p.ld_e + hq), __ldg(p.row_max + row * p.heads + hq),
+                             l > 0.f ? 1.f / l : 0.f, ci);
+        }
+        stats[row * 4 + hq] = st;
+    }
+}
+
+// HEAVY = false: warp w owns row w of the transposed CSR (source node j); rows longer than p.t_chunk are skipped when a
+//                plan is given.   HEAVY = true: warp w owns plan item w = (row, k) and writes partial d_Wh / d_er rows
+//                to p.t_ws, merged by gat_bwd_combine_node_kernel.
+// P = g rows in flight per lane (rolling: the slot of a consumed edge is refilled with edge + P of the same 32-edge
+// chunk).  First version (profiles/r02_gat_bwd_fused.txt): load 4 rows, reduce, load 4 more — ~110 warp instructions per
+// edge (per-edge head selects, 64-bit row address multiplies, zero fills), issue active 35 %, DRAM 42-55 %, every top
+// stall on the first use of a loaded row.  Now: head masks are hoisted out of the edge loop (FFMA instead of
+// ISETP+FSEL), the scoring lane computes the row's byte offset once, the chunk's first P rows are requested BEFORE the
+// scores are computed, and nothing is zero-filled (short groups are skipped by warp-uniform branches).
+template <int NV, int P>
+__global__ void __launch_bounds__(32, 16)
+gat_backward_fused_kernel(const GatBwdParams p, const float4* __restrict__ stats, float* __restrict__ dz_ws) {
+    static_assert(32 % P == 0, "window depth must divide the 32-edge chunk");
+    __shared__ long long s_off[32];
+    __shared__ float s_a[32][4];
+    __shared__ float2 s_bc[32][4];
+    __shared__ __align__(16) float s_dz[32][4];
+    const int lane = threadIdx.x;
+    // ONE launch: blocks [0, t_n_items) take the plan items of the long rows (they start first), the rest one row each —
+    // the short rows' dependent start-up round trips then overlap the long rows' streaming instead of following it
+    // (as two launches: 14.8 ms at 60 % DRAM, then 18.2 ms at 39 %; profiles/r02_gat_bwd_fused.txt)
+    const bool HEAVY = blockIdx.x < p.t_n_items;
+    const long long wid = HEAVY ? blockIdx.x : blockIdx.x - p.t_n_items;
+    const int H = p.heads, FD = p.heads * p.D;
+    long long row, beg, end;
+    if (HEAVY) {
+        const int2 it = p.t_items[wid];
+        row = it.x;
+        const long long rb = gat_rp(p.t_row_ptr, p.rp64, row), re = gat_rp(p.t_row_ptr, p.rp64, row + 1);
+        beg = rb + static_cast<long long>(it.y) * p.t_chunk;
+        end = min(re, beg + p.t_chunk);
+    } else {
+        row = wid;
+        if (row >= p.n_src) return;
+        beg = gat_rp(p.t_row_ptr, p.rp64, row);
+        end = gat_rp(p.t_row_ptr, p.rp64, row + 1);
+        if (p.t_chunk > 0 && end - beg > p.t_chunk) return;  // done by the heavy items
+    }
+    const int hq = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);   // the head whose reductions land in this lane
+
+    int hsel[NV];
+    bool von[NV];
+    float4 wh[NV];
+    float hm[NV][4];                                            // 1 where vector i belongs to head h
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * 32 + lane) * 4;
+        von[i] = c0 < FD;
+        hsel[i] = von[i] ? c0 / p.D : 0;
+        wh[i] = von[i] ? ldg_nc_f4(p.Wh + row * p.ldw + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) hm[i][h] = (von[i] && hsel[i] == h) ? 1.f : 0.f;
+    }
+    float er_j[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) er_j[h] = h < H ? __ldg(p.er + row * p.ld_e + h) : 0.f;
+
+    float acc[NV][4];
+    float4 raw[P][NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[i][a] = 0.f;
+#pragma unroll
+        for (int u = 0; u < P; ++u) raw[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);   // vectors past FD stay zero
+    }
+    float der = 0.f;
+    const char* __restrict__ gbase = reinterpret_cast<const char*>(p.g) + lane * 16;
+    const long long g_stride = p.ldg * 4;
+
+    // per-lane edge of the current chunk: destination id, forward position, destination record; ids two chunks ahead
+    int i_cur = 0, eo_cur = 0, i_nxt = 0, eo_nxt = 0;
+    float4 st[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) st[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beg + lane < end) {
+        i_cur = __ldg(p.t_col + beg + lane);
+        eo_cur = __ldg(p.perm + beg + lane);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) st[h] = __ldg(stats + static_cast<long long>(i_cur) * 4 + h);
+    }
+    if (beg + 32 + lane < end) {
+        i_nxt = __ldg(p.t_col + beg + 32 + lane);
+        eo_nxt = __ldg(p.perm + beg + 32 + lane);
+    }
+
+    for (long long e0 = beg; e0 < end; e0 += 32) {
+        const int n = static_cast<int>(min(32ll, end - e0));
+        s_off[lane] = static_cast<long long>(i_cur) * g_stride;
+        __syncwarp();
+        // the chunk's first P gradient rows leave now; the scores are computed under their latency
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            if (u < n) {
+                const char* src = gbase + s_off[u];
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (von[i]) raw[u][i] = ldg_nc_f4(reinterpret_cast<const float*>(src + i * 512));
+            }
+        }
+        // score this lane's edge for every head: aggregation weight a = alpha*mask, dz = b*dalpha - cc
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float a = 0.f, b = 0.f, cc = 0.f;
+            if (h < H && lane < n) {
+                const float z = st[h].x + er_j[h];
+                const float lz = z > 0.f ? z : p.slope * z;
+                const float alpha = expf(p.sign * lz - st[h].y) * st[h].z;
+                const float dact = p.sign * (z > 0.f ? 1.f : p.slope);
+                const float mk = p.drop_thresh ? gat_keep_scale(p.seed, eo_cur, h, H, p.drop_thresh, p.drop_scale) : 1.f;
+                a = alpha * mk;
+                b = a * dact;
+                cc = alpha * dact * st[h].w;
+            }
+            s_a[lane][h] = a;
+            s_bc[lane][h] = make_float2(b, cc);
+        }
+        const int eo_mine = eo_cur;
+        __syncwarp();
+        // next chunk's records start their round trip now; its ids were fetched a chunk ago
+        i_cur = i_nxt;
+        eo_cur = eo_nxt;
+        if (e0 + 32 + lane < end) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) st[h] = __ldg(stats + static_cast<long long>(i_cur) * 4 + h);
+        }
+        if (e0 + 64 + lane < end) {
+            i_nxt = __ldg(p.t_col + e0 + 64 + lane);
+            eo_nxt = __ldg(p.perm + e0 + 64 + lane);
+        }
+
+#pragma unroll 1
+        for (int k = 0; k < n; k += P) {
+#pragma unroll
+            for (int u = 0; u < P; ++u) {
+                const int e = k + u;
+                if (e < n) {
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const float d = raw[u][i].x * wh[i].x + raw[u][i].y * wh[i].y + raw[u][i].z * wh[i].z +
+                                        raw[u][i].w * wh[i].w;
+                        v0 = fmaf(hm[i][0], d, v0); v1 = fmaf(hm[i][1], d, v1);
+                        v2 = fmaf(hm[i][2], d, v2); v3 = fmaf(hm[i][3], d, v3);
+                    }
+                    const float dalpha = warp_sum4(v0, v1, v2, v3, lane);
+                    const float2 bc = s_bc[e][hq];
+                    const float dz = fmaf(bc.x, dalpha, -bc.y);
+                    der += dz;
+                    if ((lane & 7) == 0) s_dz[e][hq] = dz;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        const float a = s_a[e][hsel[i]];
+                        acc[i][0] = fmaf(a, raw[u][i].x, acc[i][0]);
+                        acc[i][1] = fmaf(a, raw[u][i].y, acc[i][1]);
+                        acc[i][2] = fmaf(a, raw[u][i].z, acc[i][2]);
+                        acc[i][3] = fmaf(a, raw[u][i].w, acc[i][3]);
+                    }
+                    if (e + P < n) {                             // refill the slot with edge e + P of this chunk
+                        const char* src = gbase + s_off[e + P];
+#pragma unroll
+                        for (int i = 0; i < NV; ++i)
+                            if (von[i]) raw[u][i] = ldg_nc_f4(reinterpret_cast<const float*>(src + i * 512));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < n) {   // dz of this lane's edge, all heads, at the edge's position in the forward CSR
+            if (H == 4) {
+                *reinterpret_cast<float4*>(dz_ws + static_cast<long long>(eo_mine) * 4) =
+                    *reinterpret_cast<const float4*>(&s_dz[lane][0]);
+            } else {
+                for (int h = 0; h < H; ++h) dz_ws[static_cast<long long>(eo_mine) * H + h] = s_dz[lane][h];
+            }
+        }
+        __syncwarp();  // s_* are rewritten by the next chunk
+    }
+
+    const long long FDh = FD;
+    if ((lane & 7) == 0 && hq < H) {
+        if (HEAVY) p.t_ws[wid * (FDh + H) + FDh + hq] = der;
+        else p.d_er[row * p.ld_de + hq] = der;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (!von[i]) continue;
+        const int c0 = (i * 32 + lane) * 4;
+        if (HEAVY) {
+            float* o = p.t_ws + wid * (FDh + H) + c0;
+            o[0] = acc[i][0]; o[1] = acc[i][1]; o[2] = acc[i][2]; o[3] = acc[i][3];
+        } else {
+            stg_cs_f4(p.d_Wh + row * p.ldd + c0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        }
+    }
+}
+
+// d_el_i = sum of dz over forward row i (dz_ws is [nnz, heads], CSR edge order): warp per row / per plan item
+template <bool HEAVY>
+__global__ void __launch_bounds__(128)
+gat_bwd_del_kernel(const GatBwdParams p, const float* __restrict__ dz_ws) {
+    const int lane = threadIdx.x & 31;
+    const long long unit = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int H = p.heads;
+    long long row, beg, end;
+    if (HEAVY) {
+        if (unit >= p.e_n_items) return;
+        const int2 it = p.e_items[unit];
+        row = it.x;
+        const long long rb = gat_rp(p.row_ptr, p.rp64, row), re = gat_rp(p.row_ptr, p.rp64, row + 1);
+        beg = rb + static_cast<long long>(it.y) * p.e_chunk;
+        end = min(re, beg + p.e_chunk);
+    } else {
+        row = unit;
+        if (row >= p.n_dst) return;
+        beg = gat_rp(p.row_ptr, p.rp64, row);
+        end = gat_rp(p.row_ptr, p.rp64, row + 1);
+        if (p.e_chunk > 0 && end - beg > p.e_chunk) return;
+    }
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (H == 4) {
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(dz_ws);
+        long long e = beg + lane;
+        for (; e + 96 < end; e += 128) {
+            const float4 a = __ldg(w4 + e), b = __ldg(w4 + e + 32), c = __ldg(w4 + e + 64), d = __ldg(w4 + e + 96);
+            s[0] += (a.x + b.x) + (c.x + d.x); s[1] += (a.y + b.y) + (c.y + d.y);
+            s[2] += (a.z + b.z) + (c.z + d.z); s[3] += (a.w + b.w) + (c.w + d.w);
+        }
+        for (; e < end; e += 32) {
+            const float4 a = __ldg(w4 + e);
+            s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+        }
+    } else {
+        for (long long e = beg + lane; e < end; e += 32)
+            for (int h = 0; h < H; ++h) s[h] += __ldg(dz_ws + e * H + h);
+    }
+    const float t = warp_sum4(s[0], s[1], s[2], s[3], lane);
+    const int hq = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    if ((lane & 7) == 0 && hq < H) {
+        if (HEAVY) p.e_ws[unit * H + hq] = t;
+        else p.d_el[row * p.ld_de + hq] = t;
+    }
+}
+
+template <int NV, int P>
+static int launch_gat_bwd_fused(const GatBwdParams& p, cudaStream_t st) {
+    float4* stats = nullptr;
+    DGLLB_CUDA_TRY(cudaMallocAsync(&stats, sizeof(float4) * 4 * static_cast<size_t>(p.n_dst > 0 ? p.n_dst : 1), st));
+    float* dz_ws = reinterpret_cast<float*>(p.ws);
+    int rc = DGLLB_OK;
+    do {
+        if (p.n_dst > 0) {
+            const long long blocks = (p.n_dst * 32 + 127) / 128;
+            if (blocks >= (1ll << 31)) { set_error("gat_backward: grid too large"); rc = DGLLB_ERR_INVALID; break; }
+            gat_bwd_prep_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(p, stats);
+        }
+        if (p.n_src + p.t_n_items >= (1ll << 31)) { set_error("gat_backward: grid too large"); rc = DGLLB_ERR_INVALID; break; }
+        if (p.n_src + p.t_n_items > 0)
+            gat_backward_fused_kernel<NV, P><<<static_cast<unsigned>(p.n_src + p.t_n_items), 32, 0, st>>>(p, stats, dz_ws);
+        if (p.t_n_items > 0) gat_bwd_combine_node_kernel<<<static_cast<unsigned>(p.t_n_items), 256, 0, st>>>(p);
+        if (p.e_n_items > 0)
+            gat_bwd_del_kernel<true><<<static_cast<unsigned>((p.e_n_items * 32 + 127) / 128), 128, 0, st>>>(p, dz_ws);
+        if (p.n_dst > 0)
+            gat_bwd_del_kernel<false><<<static_cast<unsigned>((p.n_dst * 32 + 127) / 128), 128, 0, st>>>(p, dz_ws);
+        if (p.e_n_items > 0) gat_bwd_combine_edge_kernel<<<static_cast<unsigned>(p.e_n_items), 32, 0, st>>>(p);
+        g_launch_count.fetch_add((p.n_dst > 0 ? 2 : 0) + (p.n_src + p.t_n_items > 0 ? 1 : 0) + (p.t_n_items > 0 ? 1 : 0) +
+                                 (p.e_n_items > 0 ? 2 : 0));
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("gat_backward: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
+    } while (0);
+    cudaFreeAsync(stats, st);
+    return rc;
+}
+
 static int gat_bwd_block_threads() {
     const int tb = opt_get(OPT_GAT_BWD_TB);  // default 64: small blocks retire evenly on ragged rows, 64.0 -> 55.9 ms (products-shaped)
     return (tb == 32 || tb == 64 || tb == 128 || tb == 256) ? tb : 64;
@@ -806,6 +1136,14 @@ static int launch_gat_bwd(GatBwdParams& p, const dgllb_csr_plan* plan, const dgl
         p.t_ws = reinterpret_cast<float*>(ws + b_e);
     }
     int rc;
+    // fused single pass over CSR^T for the whole-row shapes (option gat_bwd_kernel=twopass pins the older path)
+    const int FD = p.heads * p.D;
+    if (VE == 4 && p.heads <= 4 && FD >= 32 && FD <= 512 && opt_get(OPT_GAT_BWD_KERNEL) != 1) {
+        const int depth = opt_get(OPT_GAT_BWD_DEPTH);
+        if (FD <= 128) rc = depth == 4 ? launch_gat_bwd_fused<1, 4>(p, st) : launch_gat_bwd_fused<1, 8>(p, st);
+        else if (FD <= 256) rc = depth == 4 ? launch_gat_bwd_fused<2, 4>(p, st) : launch_gat_bwd_fused<2, 8>(p, st);
+        else rc = depth == 2 ? launch_gat_bwd_fused<4, 2>(p, st) : launch_gat_bwd_fused<4, 4>(p, st);
+    } else
     if (lanes == 8) rc = launch_gat_bwd_lanes<VE, 8>(p, nch, st);
     else if (lanes == 16) rc = launch_gat_bwd_lanes<VE, 16>(p, nch, st);
     else rc = launch_gat_bwd_lanes<VE, 32>(p, nch, st);

@@ -259,6 +259,250 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------ persistent variant --
+// The kernel above runs ONE tile per CTA: set-up, the first TMA round trip, the MMAs and the epilogue of a tile are
+// serial, and for short reductions (K = 100: four k-blocks) that chain IS the tile's time — 2,449,029 x 100 x 256 took
+// 1.50 ms against 0.54 ms of HBM time (profiles/r02_gemm.jsonl), and every second CTA re-read its A block from L2.
+// Here one CTA per SM walks tiles t = blockIdx.x, + gridDim.x, ...:
+//   * BN = 256 when N > 128: the whole N = 256 output row block in one pass, A is read once;
+//   * the TMA producer runs ahead ACROSS tiles (the smem ring does not drain at a tile boundary);
+//   * two accumulators in TMEM (2 x BN columns): the MMA warp starts tile t+1 while the epilogue warps drain tile t
+//     (tmem_full / tmem_empty barriers), so stores to C overlap the next tile's loads and MMAs;
+//   * the epilogue stages through its own shared memory (the ring is busy) for coalesced 128-byte row segments.
+// Used when there is at least one tile per SM and no split-K; same operands, descriptors and results as above.
+//   * eight epilogue warps (two per scheduler; a warp reads the TMEM lane quarter warp % 4 and every second 32-column
+//     chunk) turn their 32 x 32 chunk into a 128B-swizzled shared-memory box and ONE lane hands it to TMA
+//     (cp.async.bulk.tensor store, rows / columns past M / N clipped by the tensor map).  The first version of this
+//     kernel used four epilogue warps and per-lane LDS + STG.128 like the kernel above: one warp per scheduler with a
+//     ~400-instruction dependent chain per chunk made the EPILOGUE the bound — 1.85 ms on the K = 100 shape, slower than
+//     the one-tile kernel (ncu: issue active 17 %, tensor pipe 8 %, DRAM 23 %; profiles/r02_gemm_persistent.txt).
+//     C that TMA cannot address (unaligned, or accumulate = read-modify-write) takes the staged LDS/STG path.
+constexpr int kPEpiWarps = 8;
+constexpr int kPThreads = (4 + kPEpiWarps) * 32;
+constexpr int kPStageBytes = kPEpiWarps * 4096;                      // one 32 x 32 fp32 box per epilogue warp
+template <int BNP> struct PersistCfg {
+    static constexpr int stage_b = BNP * BK * 4;
+    static constexpr int stages = (BNP == 256) ? 4 : 6;             // 4 x 48 KB or 6 x 32 KB = 192 KB
+    static constexpr size_t smem = static_cast<size_t>(stages) * (kStageA + stage_b) + kPStageBytes + 1024;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool A_MN, bool B_MN, int BNP>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                            const __grid_constant__ CUtensorMap tmap_c, int c_by_tma, float* __restrict__ C,
+                            long long ldc, long long M, int N, int n_tiles_n, long long n_tiles, int num_kb,
+                            const float* __restrict__ bias, int epi, int accumulate) {
+    typedef PersistCfg<BNP> Cfg;
+    constexpr int S = Cfg::stages;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem_a = smem;
+    unsigned char* smem_b = smem + S * kStageA;
+    float* stage_c = reinterpret_cast<float*>(smem + S * (kStageA + Cfg::stage_b));   // 1 KB aligned (swizzle atom)
+    __shared__ uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_holder;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+        if (c_by_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_c)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], kPEpiWarps);              // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_holder, 2 * BNP);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long long it = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int n0 = static_cast<int>(t % n_tiles_n) * BNP;
+                const int m0 = static_cast<int>(t / n_tiles_n) * BM;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = static_cast<int>(it % S);
+                    const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[s], kStageA + Cfg::stage_b);
+                    const int k0 = kb * BK;
+                    unsigned char* sa = smem_a + s * kStageA;
+                    unsigned char* sb = smem_b + s * Cfg::stage_b;
+                    if (A_MN) {
+#pragma unroll
+                        for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmap_a, m0 + b * 32, k0, &full_bar[s]);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, k0, m0, &full_bar[s]);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int b = 0; b < BNP / 32; ++b) tma_load_2d(sb + b * 4096, &tmap_b, n0 + b * 32, k0, &full_bar[s]);
+                    } else {
+                        tma_load_2d(sb, &tmap_b, k0, n0, &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u) |
+                                   (static_cast<uint32_t>(BNP >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+            long long it = 0;
+            int lt = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+                const int as = lt & 1;
+                const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
+                mbar_wait(&tmem_empty_bar[as], aph ^ 1u);           // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BNP);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = static_cast<int>(it % S);
+                    const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = A_MN ? make_desc(smem_a + s * kStageA, 4096, 512, 1) : make_desc(smem_a + s * kStageA, 16, 1024, 2);
+                    const uint64_t db = B_MN ? make_desc(smem_b + s * Cfg::stage_b, 4096, 512, 1)
+                                             : make_desc(smem_b + s * Cfg::stage_b, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)
+                        tc_mma_tf32(tmem_d, da + static_cast<uint64_t>((A_MN ? 64 : 2) * k),
+                                    db + static_cast<uint64_t>((B_MN ? 64 : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty_bar[s]);
+                }
+                tc_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int q = ew & 3;                                       // TMEM lane quarter this warp may read (= warp % 4)
+        const int half = ew >> 2;                                   // it takes the chunks c = half, half + 2, ...
+        float* tile = stage_c + ew * 1024;
+        const int sw = lane & 7;                                    // swizzle term of this lane's staged row
+        int lt = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            const int as = lt & 1;
+            const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
+            const int n0 = static_cast<int>(t % n_tiles_n) * BNP;
+            const long long row0 = (t / n_tiles_n) * BM + q * 32;
+            mbar_wait(&tmem_full_bar[as], aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + static_cast<uint32_t>(as * BNP) + (static_cast<uint32_t>(q * 32) << 16);
+            constexpr int NC = BNP / 32;
+            int n_chunks = (N - n0 + 31) / 32;
+            if (n_chunks > NC) n_chunks = NC;
+            bool released = false;
+#pragma unroll 1
+            for (int c = half; c < n_chunks; c += 2) {
+                const int cbase = n0 + c * 32;
+                uint32_t r[32];
+                tmem_ld32(tacc + static_cast<uint32_t>(c * 32), r);
+                if (c + 2 >= n_chunks) {                            // this warp's part of the accumulator is read out
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+                    released = true;
+                }
+                if (c_by_tma) {
+                    if (bias || epi) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float v = __uint_as_float(r[j]);
+                            if (bias && cbase + j < N) v += __ldg(bias + cbase + j);
+                            r[j] = __float_as_uint(epi_fn(v, epi));
+                        }
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box left smem
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ sw) << 2)) =
+                            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < M) tma_store_2d(&tmap_c, tile, cbase, static_cast<int>(row0));
+                } else {
+                    const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && cbase + 32 <= N;
+                    if (vec_ok) {
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ sw) << 2)) =
+                                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        __syncwarp();
+                        const int jj = lane & 7, c4 = jj * 4;
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias) {
+                            b4.x = __ldg(bias + cbase + c4); b4.y = __ldg(bias + cbase + c4 + 1);
+                            b4.z = __ldg(bias + cbase + c4 + 2); b4.w = __ldg(bias + cbase + c4 + 3);
+                        }
+#pragma unroll
+                        for (int i8 = 0; i8 < 8; ++i8) {
+                            const int rr = i8 * 4 + (lane >> 3);
+                            const long long grow = row0 + rr;
+                            if (grow < M) {
+                                float4 v = *reinterpret_cast<const float4*>(tile + rr * 32 + ((jj ^ (rr & 7)) << 2));
+                                float* dst = C + grow * ldc + cbase + c4;
+                                if (accumulate) {
+                                    const float4 o = *reinterpret_cast<const float4*>(dst);
+                                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                                }
+                                v.x = epi_fn(v.x + b4.x, epi); v.y = epi_fn(v.y + b4.y, epi);
+                                v.z = epi_fn(v.z + b4.z, epi); v.w = epi_fn(v.w + b4.w, epi);
+                                *reinterpret_cast<float4*>(dst) = v;
+                            }
+                        }
+                    } else {
+                        const long long row = row0 + lane;
+                        if (row < M) {
+                            float* crow = C + row * ldc;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int col = cbase + j;
+                                if (col < N) {
+                                    float v = __uint_as_float(r[j]);
+                                    if (accumulate) v += crow[col];
+                                    if (bias) v += __ldg(bias + col);
+                                    crow[col] = epi_fn(v, epi);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (!released) {                                        // no chunk of this tile was this warp's
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+            }
+        }
+        if (c_by_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * BNP);
+}
+
 // dst[r, 0:cols] = src[r, 0:cols], dst row stride ldd (a multiple of 4 floats), pad columns zero
 __global__ void __launch_bounds__(256)
 align_copy_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd, long long rows,
@@ -347,6 +591,36 @@ static void launch(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& t
                                                                bias, epi, accumulate);
 }
 
+template <bool A_MN, bool B_MN, int BNP>
+static cudaError_t launch_persistent(int grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
+                                     const CUtensorMap& tc, int c_by_tma, float* C, long long ldc, long long M, int N, int n_tiles_n, long long n_tiles, int num_kb,
+                                     const float* bias, int epi, int accumulate) {
+    static std::once_flag once[64];
+    static cudaError_t err[64];
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    const int slot = dev_id & 63;
+    std::call_once(once[slot], [&]() {
+        err[slot] = cudaFuncSetAttribute(gemm_tf32_persistent_kernel<A_MN, B_MN, BNP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(PersistCfg<BNP>::smem));
+    });
+    if (err[slot] != cudaSuccess) return err[slot];
+    gemm_tf32_persistent_kernel<A_MN, B_MN, BNP><<<grid, kPThreads, PersistCfg<BNP>::smem, st>>>(
+        ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+    return cudaSuccess;
+}
+
+template <int BNP>
+static cudaError_t launch_persistent_mn(bool a_mn, bool b_mn, int grid, cudaStream_t st, const CUtensorMap& ta,
+                                        const CUtensorMap& tb, const CUtensorMap& tc, int c_by_tma, float* C, long long ldc, long long M, int N, int n_tiles_n,
+                                        long long n_tiles, int num_kb, const float* bias, int epi, int accumulate) {
+    if (a_mn && b_mn) return launch_persistent<true, true, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+    if (a_mn) return launch_persistent<true, false, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+    if (b_mn) return launch_persistent<false, true, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+    return launch_persistent<false, false, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+}
+
 }  // namespace tf32
 
 int gemm_tf32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
@@ -402,6 +676,33 @@ int gemm_tf32(const float* A, long long lda, int transA, const float* B, long lo
         CUtensorMap ta, tb;
         const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
         if ((rc = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK, sw_mn) : make_tmap(&ta, A, K, M, lda, BK, BM, sw_k)) != DGLLB_OK) break;
+        // persistent kernel (one CTA per SM, BN = 256 when N > 128, two accumulators): at least one tile per SM
+        {
+            // BN = 256 reads A once per row block, but pads N to a multiple of 256: keep it only while that costs < 10 %
+            // more columns than 128-wide tiles would (N = 602: 768 vs 640 columns -> 128)
+            const long long pad256 = (N + 255) / 256 * 256, pad128 = (N + 127) / 128 * 128;
+            const int bnp = (N > 128 && pad256 * 10 <= pad128 * 11) ? 256 : 128;
+            const long long p_tiles_m = (M + BM - 1) / BM;
+            const int p_tiles_n = static_cast<int>((N + bnp - 1) / bnp);
+            const long long p_tiles = p_tiles_m * p_tiles_n;
+            const int gk = opt_get(OPT_GEMM_KERNEL);   // 3 pins the one-tile-per-CTA kernel, 4 the persistent one
+            if ((p_tiles >= di.sm_count || gk == 4) && gk != 3 && p_tiles_m < (1ll << 24)) {
+                if ((rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK, sw_mn) : make_tmap(&tb, B, K, N, ldb, BK, bnp, sw_k)) != DGLLB_OK) break;
+                const int grid_p = static_cast<int>(p_tiles < di.sm_count ? p_tiles : di.sm_count);
+                const int nkb = static_cast<int>((K + BK - 1) / BK);
+                // C goes out by TMA store when the tensor map can address it and nothing has to be read back
+                CUtensorMap tc = ta;
+                const int c_by_tma = (tma_ok(C, ldc) && !accumulate) ? 1 : 0;
+                if (c_by_tma && (rc = make_tmap(&tc, C, N, M, ldc, 32, 32, sw_k)) != DGLLB_OK) break;
+                cudaError_t e = bnp == 256
+                    ? launch_persistent_mn<256>(a_mn, b_mn, grid_p, st, ta, tb, tc, c_by_tma, C, ldc, M, static_cast<int>(N), p_tiles_n, p_tiles, nkb, bias, epi, accumulate)
+                    : launch_persistent_mn<128>(a_mn, b_mn, grid_p, st, ta, tb, tc, c_by_tma, C, ldc, M, static_cast<int>(N), p_tiles_n, p_tiles, nkb, bias, epi, accumulate);
+                if (e == cudaSuccess) e = cudaGetLastError();
+                if (e != cudaSuccess) { set_error("gemm: persistent launch failed: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
+                g_launch_count.fetch_add(1);
+                break;
+            }
+        }
         if ((rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK, sw_mn) : make_tmap(&tb, B, K, N, ldb, BK, BN, sw_k)) != DGLLB_OK) break;
         const size_t smem = static_cast<size_t>(kStages) * (kStageA + kStageB) + 1024;
         static std::once_flag attr_once[64];

@@ -38,6 +38,8 @@ struct SpmmParams {
     const int2* heavy_items;  // (row, chunk)
     long long n_heavy_items;
     int chunk_edges;          // 0 = no plan
+    float* heavy_ws;          // [n_heavy_items, ld_hws] partial rows of the split rows (merged in chunk order)
+    long long ld_hws;
     const int* row_cnt;       // optional per-row edge-count clamp (legacy num_neighbors)
     long long nnz_hint;       // host-known upper bound on row_ptr[n_dst]; < 0 = unknown
     int out_vec;              // out rows are 16-byte aligned: 128-bit stores / RED.ADD.128 allowed

@@ -42,7 +42,7 @@ static SpmmParams make_params(const int* row_ptr, const int* col, const float* v
     p.row_ptr = row_ptr; p.rp64 = 0; p.col = col; p.vals = vals; p.X = X; p.ldx = ldx;
     p.out = out; p.ldo = ldo; p.n_dst = n; p.F = F; p.n_slabs = 1; p.mean = 0;
     p.row_scale = nullptr; p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.epi = epi;
-    p.argmax = nullptr; p.heavy_items = nullptr; p.n_heavy_items = 0; p.chunk_edges = 0;
+    p.argmax = nullptr; p.heavy_items = nullptr; p.n_heavy_items = 0; p.chunk_edges = 0; p.heavy_ws = nullptr; p.ld_hws = 0;
     p.row_cnt = row_cnt;
     p.nnz_hint = -1;
     p.out_vec = 0;

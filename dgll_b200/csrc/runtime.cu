@@ -60,6 +60,7 @@ int get_devinfo(DevInfo* out) {
 struct OptDesc { const char* name; const char* env; const char* const* words; };
 static const char* const kSpmmWords[] = {"auto", "rowsplit", "stream", "wholerow", nullptr};
 static const char* const kGatWords[] = {"auto", "group", "row", nullptr};
+static const char* const kGatBwdWords[] = {"auto", "twopass", "fused", nullptr};
 static const OptDesc kOpts[OPT_COUNT] = {
     {"spmm_kernel", "DGLLB_SPMM_KERNEL", kSpmmWords},
     {"spmm_tb", "DGLLB_SPMM_TB", nullptr},
@@ -70,6 +71,8 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"gat_kernel", "DGLLB_GAT_KERNEL", kGatWords},
     {"gat_row_warps", "DGLLB_GAT_ROW_WARPS", nullptr},
     {"gat_bwd_tb", "DGLLB_GAT_BWD_TB", nullptr},
+    {"gat_bwd_kernel", "DGLLB_GAT_BWD_KERNEL", kGatBwdWords},
+    {"gat_bwd_depth", "DGLLB_GAT_BWD_DEPTH", nullptr},
     {"bin_tb", "DGLLB_BIN_TB", nullptr},
     {"gemm_kernel", "DGLLB_GEMM_KERNEL", nullptr},
     {"nvtx", "DGLLB_NVTX", nullptr},

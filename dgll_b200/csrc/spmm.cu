@@ -133,8 +133,9 @@ spmm_rowslab_kernel(const SpmmParams p) {
     long long row, beg, end, deg;
     int slab;
     bool heavy = false;
+    long long it = 0;
     if (group < n_heavy_groups) {
-        const long long it = group / p.n_slabs;
+        it = group / p.n_slabs;
         slab = static_cast<int>(group - it * p.n_slabs);
         const int2 hc = p.heavy_items[it];
         row = hc.x;
@@ -237,14 +238,17 @@ spmm_rowslab_kernel(const SpmmParams p) {
     const int valid = min(A, p.F - col0);
 
     if (heavy) {
-        // partial sums of a split row: combine with RED.ADD (rows were pre-zeroed);
-        // epilogue runs in spmm_finalize_heavy_kernel.
-        if (A == 4 && valid == 4 && p.out_vec) {
-            atomicAdd(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        // partial sums of a split row go to the item's workspace row; spmm_finalize_heavy_kernel adds the chunks of a
+        // row in chunk order and runs the epilogue (round 1 used RED.ADD here: heavy-row sums were not reproducible)
+        float* __restrict__ w = p.heavy_ws + it * p.ld_hws + col0;
+        if (A % 4 == 0 && valid == A) {
+#pragma unroll
+            for (int a = 0; a < A; a += 4)
+                *reinterpret_cast<float4*>(w + a) = make_float4(acc[a], acc[a + 1], acc[a + 2], acc[a + 3]);
         } else {
 #pragma unroll
             for (int a = 0; a < A; ++a)
-                if (a < valid) atomicAdd(o + a, acc[a]);
+                if (a < valid) w[a] = acc[a];
         }
         return;
     }
@@ -434,27 +438,23 @@ spmm_stream_kernel(const SpmmParams p, const int T, const long long n_chunks) {
     }
 }
 
-// zero the output rows of split rows before the RED.ADDs land
-__global__ void spmm_zero_heavy_kernel(const int* heavy_rows, long long n_heavy, float* out,
-                                       long long ldo, int F) {
-    const long long r = blockIdx.x;
-    if (r >= n_heavy) return;
-    float* o = out + static_cast<long long>(heavy_rows[r]) * ldo;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) o[f] = 0.f;
-}
-
-__global__ void spmm_finalize_heavy_kernel(const int* heavy_rows, long long n_heavy, float* out,
-                                           long long ldo, int F, const float* addend,
-                                           long long ld_add, const float* bias, int epi) {
-    const long long r = blockIdx.x;
-    if (r >= n_heavy) return;
-    const long long row = heavy_rows[r];
-    float* o = out + row * ldo;
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        float v = o[f];
-        if (addend) v += addend[row * ld_add + f];
-        if (bias) v += bias[f];
-        o[f] = apply_epi(v, epi);
+// merge the partial rows of every split row: one block per k == 0 item (its chunks are items [w, w + nc)), fixed order
+__global__ void spmm_finalize_heavy_kernel(const SpmmParams p) {
+    const long long w = blockIdx.x;
+    if (w >= p.n_heavy_items) return;
+    const int2 it = p.heavy_items[w];
+    if (it.y != 0) return;
+    const long long row = it.x;
+    const long long deg = load_rp(p.row_ptr, p.rp64, row + 1) - load_rp(p.row_ptr, p.rp64, row);
+    const int nc = static_cast<int>((deg + p.chunk_edges - 1) / p.chunk_edges);
+    float* o = p.out + row * p.ldo;
+    const float* base = p.heavy_ws + w * p.ld_hws;
+    for (int f = threadIdx.x; f < p.F; f += blockDim.x) {
+        float v = 0.f;
+        for (int c = 0; c < nc; ++c) v += base[static_cast<long long>(c) * p.ld_hws + f];
+        if (p.addend) v += p.addend[row * p.ld_add + f];
+        if (p.bias) v += p.bias[f];
+        o[f] = apply_epi(v, p.epi);
     }
 }
 
@@ -630,9 +630,9 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
         p.heavy_items = plan->items;
         p.n_heavy_items = plan->n_items;
         p.chunk_edges = plan->chunk_edges;
-        spmm_zero_heavy_kernel<<<static_cast<unsigned>(plan->n_heavy_rows), 128, 0, st>>>(
-            plan->heavy_rows, plan->n_heavy_rows, p.out, p.ldo, p.F);
-        DGLLB_LAUNCH_CHECK();
+        p.ld_hws = (static_cast<long long>(p.F) + 7) / 8 * 8;
+        DGLLB_REQUIRE(plan->n_items < (1ll << 31), "spmm: too many plan items");
+        DGLLB_CUDA_TRY(cudaMallocAsync(&p.heavy_ws, sizeof(float) * static_cast<size_t>(plan->n_items) * p.ld_hws, st));
     }
     int rc;
     p.out_vec = aligned16(p.out) && (p.ldo % 4 == 0);
@@ -661,13 +661,16 @@ int spmm_run(SpmmParams& p, int x_dtype, bool is_max, const dgllb_csr_plan* plan
         else rc = vec ? launch_spmm_lanes<__nv_bfloat16, 8>(p, is_max, st)
                       : launch_spmm_lanes<__nv_bfloat16, 1>(p, is_max, st);
     }
-    if (rc != DGLLB_OK) return rc;
-    if (use_plan && (p.addend || p.bias || p.epi)) {
-        spmm_finalize_heavy_kernel<<<static_cast<unsigned>(plan->n_heavy_rows), 128, 0, st>>>(
-            plan->heavy_rows, plan->n_heavy_rows, p.out, p.ldo, p.F, p.addend, p.ld_add, p.bias, p.epi);
-        DGLLB_LAUNCH_CHECK();
+    if (use_plan) {
+        if (rc == DGLLB_OK) {
+            spmm_finalize_heavy_kernel<<<static_cast<unsigned>(plan->n_items), 128, 0, st>>>(p);
+            g_launch_count.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { set_error("spmm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
+        }
+        cudaFreeAsync(p.heavy_ws, st);
     }
-    return DGLLB_OK;
+    return rc;
 }
 }  // namespace dgllb
 
@@ -712,6 +715,8 @@ extern "C" int dgllb_spmm_csr(const void* row_ptr, int row_ptr_is64, const int32
     p.heavy_items = nullptr;
     p.n_heavy_items = 0;
     p.chunk_edges = 0;
+    p.heavy_ws = nullptr;
+    p.ld_hws = 0;
     p.row_cnt = nullptr;
     p.nnz_hint = nnz;
     return spmm_run(p, x_dtype, reduce == DGLLB_MAX, plan, st);

@@ -72,7 +72,8 @@ class PipelinedSageTrainer:
     gradient all-reduce (default group when initialised; world 1 = no collective)."""
 
     def __init__(self, model, opt, labels, row_ptr, col_idx, n_feat, table=None, sharded=None, batch_size=1024,
-                 fanouts=(25, 10), group=None, precision=None, rng_seed=0, label_offset=0, max_seeds=None):
+                 fanouts=(25, 10), group=None, precision=None, rng_seed=0, label_offset=0, max_seeds=None,
+                 train_priority=True):
         if len(fanouts) != 2 or len(model.layers) != 2:
             raise ValueError("PipelinedSageTrainer: 2-layer models / two fanouts")
         if (table is None) == (sharded is None):
@@ -86,6 +87,7 @@ class PipelinedSageTrainer:
         self.B, self.f0, self.f1 = int(batch_size), int(fanouts[0]), int(fanouts[1])
         self.label_offset = int(label_offset)
         self._precision = precision
+        self._train_priority = bool(train_priority)
         dev = labels.device
         src = table if table is not None else sharded.table
         self._tdtype = src.dtype
@@ -215,10 +217,14 @@ class PipelinedSageTrainer:
         self._rng_off.copy_(keep[1])
         self.loss_sum.zero_()
         self._side = torch.cuda.Stream()
+        # the training branch is the critical path of a step (its last kernels are the all-reduce and Adam): it is captured
+        # on a HIGH-priority stream, so that when both branches have blocks waiting the SMs go to the training kernels and
+        # the produce branch (whose sharded aggregation holds SMs while its loads cross NVLink) fills what is left
+        self._main = torch.cuda.Stream(priority=-1) if self._train_priority else torch.cuda.Stream()
         self.graphs = []
         for k in range(2):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._main):
                 cur = torch.cuda.current_stream()
                 self._side.wait_stream(cur)
                 with torch.cuda.stream(self._side):

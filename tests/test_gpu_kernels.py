@@ -118,6 +118,20 @@ def test_spmm_plan_heavy_rows(K, chunk):
         out = K.spmm_csr(dev(rp), dev(col), dev(x), values=dev(vals), reduce=reduce, bias=dev(bias), relu=True,
                          plan=plan)
         assert rel_err(out.cpu().numpy(), ref) <= FP32_TOL
+        # split rows are merged in chunk order from a workspace (no atomics): run-to-run bit-identical, also for an
+        # output whose rows are not 16-byte aligned and for bf16 features
+        for _ in range(3):
+            assert torch.equal(K.spmm_csr(dev(rp), dev(col), dev(x), values=dev(vals), reduce=reduce, bias=dev(bias),
+                                          relu=True, plan=plan), out)
+        odd = torch.zeros((n_dst, F + 1), device="cuda")[:, 1:]
+        K.spmm_csr(dev(rp), dev(col), dev(x), values=dev(vals), reduce=reduce, bias=dev(bias), relu=True, plan=plan,
+                   out=odd)
+        assert torch.equal(odd, out)
+        xb = dev(x).to(torch.bfloat16)
+        ob = K.spmm_csr(dev(rp), dev(col), xb, values=dev(vals), reduce=reduce, plan=plan)
+        assert torch.equal(K.spmm_csr(dev(rp), dev(col), xb, values=dev(vals), reduce=reduce, plan=plan), ob)
+        assert rel_err(ob.cpu().numpy(), oracle.spmm_csr(rp, col, xb.float().cpu().numpy(), values=vals,
+                                                         reduce=reduce)) <= FP32_TOL
 
 
 def test_spmm_bf16_features(K):
@@ -404,6 +418,61 @@ def test_gat_backward_with_row_splitting_plans(K, heads, D, mode):
                         mode=mode, dropout=0.4, seed=5, plan=plan, t_plan=t_plan)
     for a, b in zip(g2, b2):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize("heads,D", [(4, 64), (3, 16), (1, 32), (2, 128), (4, 128), (2, 20)])
+@pytest.mark.parametrize("mode", ["softmax", "exp_neg"])
+def test_gat_backward_fused_single_pass(K, heads, D, mode):
+    """The single-pass backward over the transposed CSR (whole-row shapes; option gat_bwd_kernel) on a NON-square graph
+    with long rows on both sides, with and without plans and attention dropout: fp64 autograd of the same definition
+    (<= 2e-5), the two-pass kernels (<= 2e-5), run-to-run bit-identical."""
+    rng = np.random.default_rng(7 * heads + D)
+    n_dst, n_src = 250, 400
+    rp, col = rand_csr(rng, n_dst, n_src, 24, heavy=[(3, 300), (77, 97)])
+    col[rng.random(col.size) < 0.25] = 5                    # a hub source: long row of the transposed CSR
+    wh = rng.standard_normal((n_src, heads * D)).astype(np.float32)
+    el = rng.standard_normal((n_dst, heads)).astype(np.float32)
+    er = rng.standard_normal((n_src, heads)).astype(np.float32)
+    g = rng.standard_normal((n_dst, heads * D)).astype(np.float32)
+    drp, dcol = dev(rp), dev(col)
+    trp, tcol, _, perm = K.csr_transpose(drp, dcol, n_src, want_perm=True)
+    plan, t_plan = K.CsrPlan(drp, chunk_edges=32), K.CsrPlan(trp, chunk_edges=32)
+    assert plan.n_heavy_rows == 2 and t_plan.n_heavy_rows >= 1
+    rows = torch.from_numpy(np.repeat(np.arange(n_dst), rp[1:] - rp[:-1])).long()
+    cols = torch.from_numpy(col).long()
+    for drop in (0.0, 0.4):
+        out, rmax, rsum = K.gat_forward(drp, dcol, dev(wh), dev(el), dev(er), heads, 0.2, mode=mode, save_stats=True,
+                                        dropout=drop, seed=9)
+        mask = K.gat_dropout_mask(9, col.size, heads, drop).cpu().double() if drop else torch.ones(col.size, heads).double()
+        twh = torch.from_numpy(wh).double().requires_grad_(True)
+        tel = torch.from_numpy(el).double().requires_grad_(True)
+        ter = torch.from_numpy(er).double().requires_grad_(True)
+        z = torch.nn.functional.leaky_relu(tel[rows] + ter[cols], 0.2)
+        sc = z if mode == "softmax" else -z
+        smax = torch.full((n_dst, heads), -float("inf"), dtype=torch.float64).scatter_reduce(
+            0, rows[:, None].expand(-1, heads), sc.detach(), reduce="amax")
+        ex = torch.exp(sc - smax[rows])
+        den = torch.zeros(n_dst, heads, dtype=torch.float64).index_add_(0, rows, ex)
+        alpha = ex / den[rows] * mask
+        msg = alpha[:, :, None] * twh[cols].view(-1, heads, D)
+        out_ref = torch.zeros(n_dst, heads, D, dtype=torch.float64).index_add_(0, rows, msg).view(n_dst, heads * D)
+        assert rel_err(out.cpu().numpy(), out_ref.detach().numpy()) <= FP32_TOL
+        out_ref.backward(torch.from_numpy(g).double())
+        ref = (twh.grad.numpy(), tel.grad.numpy(), ter.grad.numpy())
+        args = (drp, dcol, trp, tcol, perm, dev(wh), dev(el), dev(er), out, rmax, rsum, dev(g), heads, 0.2)
+        try:
+            K.set_option("gat_bwd_kernel", "twopass")
+            two = K.gat_backward(*args, mode=mode, dropout=drop, seed=9)
+            K.set_option("gat_bwd_kernel", "fused")
+            for pl, tpl in ((None, None), (plan, t_plan), (plan, None), (None, t_plan)):
+                got = K.gat_backward(*args, mode=mode, dropout=drop, seed=9, plan=pl, t_plan=tpl)
+                again = K.gat_backward(*args, mode=mode, dropout=drop, seed=9, plan=pl, t_plan=tpl)
+                for a, b, c, r in zip(got, two, again, ref):
+                    assert rel_err(a.cpu().numpy(), r) <= 2e-5
+                    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
+                    assert torch.equal(a, c)
+        finally:
+            K.set_option("gat_bwd_kernel", None)
 
 
 # ------------------------------------------------------------ transpose -----
@@ -713,6 +782,47 @@ def test_gemm_tcgen05_tf32_parity_all_orientations(K, M, N, K_):
     assert rel_err(o.cpu().numpy(), acc + ref) <= TF32_TOL
     # deterministic
     assert torch.equal(K.gemm(da, db, precision="tf32"), outs[0])
+
+
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (300, 64, 50), (1000, 256, 602), (17, 5, 3), (129, 130, 65),
+                                    (4096, 300, 256), (40000, 256, 100), (20000, 172, 256), (30000, 100, 256)])
+def test_gemm_tf32_persistent_kernel(K, M, N, K_):
+    """The persistent TF32 kernel (one CTA per SM walking tiles, BN = 256 when N > 128, two TMEM accumulators; option
+    gemm_kernel=4 pins it, 3 pins the one-tile-per-CTA kernel): all four operand orientations, epilogue, accumulate,
+    ragged edges, several tiles per CTA.  Same bar as the one-tile kernel, and bit-identical to it (same k order)."""
+    rng = np.random.default_rng(M + 5 * N)
+    a = rng.standard_normal((M, K_)).astype(np.float32)
+    b = rng.standard_normal((K_, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    da, db = dev(a), dev(b)
+    at, bt = da.t().contiguous(), db.t().contiguous()
+    try:
+        K.set_option("gemm_kernel", "3")
+        one = K.gemm(da, db, precision="tf32")
+        K.set_option("gemm_kernel", "4")
+        outs = [K.gemm(da, db, precision="tf32"), K.gemm(at, db, trans_a=True, precision="tf32"),
+                K.gemm(da, bt, trans_b=True, precision="tf32"),
+                K.gemm(at, bt, trans_a=True, trans_b=True, precision="tf32")]
+        for o in outs:
+            assert rel_err(o.cpu().numpy(), ref) <= TF32_TOL
+            assert torch.equal(o, outs[0])
+        if K_ < 512:                                            # above that the one-tile kernel may split K
+            assert torch.equal(outs[0], one)
+        out = K.gemm(da, db, bias=dev(bias), relu=True, precision="tf32").cpu().numpy()
+        assert rel_err(out, np.maximum(ref + bias, 0)) <= TF32_TOL
+        acc = rng.standard_normal((M, N)).astype(np.float32)
+        o = dev(acc)
+        K.gemm(da, db, out=o, accumulate=True, precision="tf32")
+        assert rel_err(o.cpu().numpy(), acc + ref) <= TF32_TOL
+        ld_c = (N + 3) // 4 * 4 + 4                             # output rows with a 16-byte-multiple stride
+        oc = torch.zeros((M, ld_c), device="cuda")
+        K.gemm(da, db, out=oc[:, :N], precision="tf32")
+        assert torch.equal(oc[:, :N], outs[0]) and float(oc[:, N:].abs().max()) == 0.0
+    finally:
+        K.set_option("gemm_kernel", None)
+    # default dispatch (persistent when there is a tile per SM) gives the same result
+    assert torch.equal(K.gemm(da, db, precision="tf32"), outs[0]) or K_ >= 512
 
 
 def test_layers_run_on_the_tf32_path():

@@ -212,24 +212,46 @@ def main():
         trp, tcol, _, perm = K.csr_transpose(rp, col, Np, want_perm=True)
         gout = torch.randn_like(wh)
         ms_t = timeit(lambda: K.csr_transpose(rp, col, Np, want_perm=True), 3)
-        ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2), 5)
-        # bytes: pass 1 reads Wh_j + writes 8 B/(edge, head); pass 2 reads g_i + 8 B/(edge, head) per transposed edge
-        bwd_bytes = nnz * (4 + heads * D * 4 + heads * 8) * 2 + Np * (heads * D * 4) * 3
-        report("gat_backward (2 passes, no atomics)", "products-shaped", ms, bwd_bytes, {"csr_transpose_ms_once": round(ms_t, 3)})
-        tplan = K.CsrPlan(trp, chunk_edges=1024)
-        for ce in (1024, 256):
-            pl, tpl = K.CsrPlan(rp, chunk_edges=ce), K.CsrPlan(trp, chunk_edges=ce)
+        # two-pass backward (round 1): pass 1 reads Wh_j + writes 8 B/(edge, head); pass 2 reads g_i + 8 B/(edge, head)
+        bytes_two = nnz * (4 + heads * D * 4 + heads * 8) * 2 + Np * (heads * D * 4) * 3
+        # fused single pass over CSR^T (round 2): per edge t_col + perm + one g_i row + the 64-byte destination record +
+        # dz written once and read once; per node g, out (pre-pass), Wh_j, d_Wh_j
+        bytes_fused = nnz * (8 + heads * D * 4 + 64 + heads * 8) + Np * (heads * D * 4) * 4 + Np * 64
+        for fam, nb in (("twopass", bytes_two), ("fused", bytes_fused)):
+            K.set_option("gat_bwd_kernel", fam)
+            ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2), 5)
+            report("gat_backward[%s, no plans]" % fam, "products-shaped", ms, nb, {"csr_transpose_ms_once": round(ms_t, 3)})
+            for ce in (1024, 256):
+                pl, tpl = K.CsrPlan(rp, chunk_edges=ce), K.CsrPlan(trp, chunk_edges=ce)
+                ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
+                                                   plan=pl, t_plan=tpl), 5)
+                report("gat_backward[%s, plans %d]" % (fam, ce), "products-shaped", ms, nb,
+                       {"heavy_rows": pl.n_heavy_rows, "chunks": pl.n_chunks, "t_heavy_rows": tpl.n_heavy_rows,
+                        "t_chunks": tpl.n_chunks})
+        K.set_option("gat_bwd_kernel", "fused")
+        pl, tpl = K.CsrPlan(rp, chunk_edges=256), K.CsrPlan(trp, chunk_edges=256)
+        for depth in ("4", "8"):
+            K.set_option("gat_bwd_depth", depth)
             ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
                                                plan=pl, t_plan=tpl), 5)
-            report("gat_backward[plans %d]" % ce, "products-shaped", ms, bwd_bytes,
-                   {"heavy_rows": pl.n_heavy_rows, "chunks": pl.n_chunks, "t_heavy_rows": tpl.n_heavy_rows,
-                    "t_chunks": tpl.n_chunks})
-        ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
-                                           plan=gplan), 5)
-        report("gat_backward[plan pass 1 only]", "products-shaped", ms, bwd_bytes)
-        ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2,
-                                           t_plan=tplan), 5)
-        report("gat_backward[plan pass 2 only]", "products-shaped", ms, bwd_bytes)
+            report("gat_backward[fused, plans 256, %s rows in flight]" % depth, "products-shaped", ms, bytes_fused)
+        K.set_option("gat_bwd_depth", None)
+        K.set_option("gat_bwd_kernel", None)
+        # the uniform control graph of the same (N, nnz): no skew, no plans
+        del rp, col, trp, tcol, perm
+        rp, col = G.uniform_csr(Np, nnz // Np, seed=3, device=dev)
+        trp, tcol, _, perm = K.csr_transpose(rp, col, Np, want_perm=True)
+        o2, rmax, rsum = K.gat_forward(rp, col, wh, el, er, heads, 0.2, save_stats=True)
+        nz = col.numel()
+        ms = timeit(lambda: K.gat_forward(rp, col, wh, el, er, heads, 0.2, out=out), args.iters)
+        report("gat_forward[row]", "uniform control N=%d nnz=%d" % (Np, nz), ms,
+               nz * (4 + heads * D * 4 + heads * 4) + Np * (heads * D * 4 + heads * 4 + 8))
+        for fam, per_edge in (("twopass", (4 + heads * D * 4 + heads * 8) * 2), ("fused", 8 + heads * D * 4 + 64 + heads * 8)):
+            K.set_option("gat_bwd_kernel", fam)
+            ms = timeit(lambda: K.gat_backward(rp, col, trp, tcol, perm, wh, el, er, o2, rmax, rsum, gout, heads, 0.2), 5)
+            report("gat_backward[%s]" % fam, "uniform control N=%d nnz=%d" % (Np, nz), ms,
+                   nz * per_edge + Np * (heads * D * 4) * (3 if fam == "twopass" else 4))
+        K.set_option("gat_bwd_kernel", None)
 
 
 if __name__ == "__main__":
