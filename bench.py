@@ -359,16 +359,29 @@ def extra_partitioned(args, rank, world, dev, barrier):
     labels = torch.randint(0, C, (hi - lo,), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
     n_train = int(1207179 * scale)
     per_rank = max(n_train // world, 64 * BATCH)
-    seeds = lo + torch.randperm(hi - lo, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))[:per_rank]
+    seeds_any = lo + torch.randperm(hi - lo, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))[:per_rank]
+    # Training seeds: papers100M's labelled nodes are arXiv papers with real citation lists, while a uniformly drawn node
+    # of an R-MAT graph of this size mostly has 0-2 in-neighbours (a 1,024-seed batch then carries ~10 K input-layer edges
+    # instead of ~200 K).  The seeds are therefore drawn uniformly among this rank's nodes with in-degree >= fanout[1],
+    # so that the output-layer block is full-size; the any-node variant is kept beside it.
+    cand = ((row_ptr[lo + 1:hi + 1] - row_ptr[lo:hi]) >= FANOUTS[1]).nonzero().flatten()
+    n_cand = int(cand.numel())
+    pick = torch.randperm(n_cand, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))[:per_rank]
+    seeds = lo + cand[pick]
+    if seeds.numel() < per_rank:                              # not enough candidates (tiny scaled-down runs): top up
+        seeds = torch.cat([seeds, seeds_any[:per_rank - seeds.numel()]])
+    del cand, pick
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
     out = {"graph": "R-MAT (0.57,0.19,0.19,0.05), N=%d nnz=%d max in-degree %d, topology replicated" % (N, NNZ, max_deg),
            "features": "F=%d fp32, node-range partitioned: %d rows (%.1f GB) per GPU" % (F, hi - lo, (hi - lo) * F * 4 / 1e9),
            "model": "GraphSAGE-mean 2-layer %d-256-%d, fanout 25/10, batch 1024 per GPU, Adam, tcgen05 TF32 transforms (fp32 operands read in place by TMA)" % (F, C),
            "train_seeds": n_train, "scaling": "weak per step (1,024 seeds per GPU); the epoch is the fixed 1,207,179 seeds",
+           "seed_choice": "uniform among the nodes with in-degree >= %d (%d candidates on rank 0's range); "
+                          "'peer_fp32_any_node_seeds' draws from all nodes instead" % (FANOUTS[1], n_cand),
            "setup_s": round(setup_s, 1), "mechanisms": {}}
 
-    def run_peer(tbl, tag, row_ptr=row_ptr, col=col):
+    def run_peer(tbl, tag, row_ptr=row_ptr, col=col, seeds=seeds):
         sharded = P.PeerShardedTable(N, tbl)
         torch.manual_seed(args.seed)
         model = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
@@ -526,6 +539,7 @@ def extra_partitioned(args, rank, world, dev, barrier):
 
     for tag, fn in (("peer_fp32", lambda: run_peer(table, "peer_fp32")), ("nccl_all_to_all", run_nccl),
                     ("peer_bf16_table", lambda: run_peer(table.to(torch.bfloat16), "peer_bf16_table")),
+                    ("peer_fp32_any_node_seeds", lambda: run_peer(table, "peer_fp32_any_node_seeds", seeds=seeds_any)),
                     ("peer_fp32_uniform_control_graph", run_uniform_control)):
         try:
             fn()
@@ -641,6 +655,18 @@ def main():
     ms, k_ms = timed_loop(step, args.steps, 0, profile=prof)
     launches = _lib.launch_count() - l0
     total_bytes = sum(batches[s % N_BATCHES]["bytes"] for s in range(args.steps))
+    # supporting figure: the dominant kernel alone, the distinct mini-batches back to back between ONE event pair — an
+    # event pair around a single ~85 us launch also counts the launch gap on both sides (ncu on the same launch: 80 us)
+    bb0, bb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bb_reps = 4
+    bb0.record()
+    for _ in range(bb_reps):
+        for bt in batches:
+            K.spmm_csr(bt["rp0"], bt["col0"], view, reduce="mean", out=bt["agg0"])
+    bb1.record()
+    torch.cuda.synchronize()
+    k_ms_bb = bb0.elapsed_time(bb1) / (bb_reps * N_BATCHES)
+    k_bytes_bb = sum(bt["bytes0"] for bt in batches) / N_BATCHES
     k_bytes = sum(batches[s % N_BATCHES]["bytes0"] for s in range(0, args.steps, 4)) / len(range(0, args.steps, 4))
 
     # ---- end to end: blocks in pinned host memory -> H2D -> kernels -> D2H of the layer-1 aggregate -----
@@ -868,6 +894,10 @@ def main():
                      "traffic": traffic, "traffic_source": "%s (ncu --set full)" % traffic_src if traffic_src else None,
                      "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / peak) if traffic else None,
                      "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": k_bytes,
+                     "back_to_back": {"kernel_ms": k_ms_bb, "achieved": k_bytes_bb / (k_ms_bb * 1e-3) / 1e9,
+                                      "dram_frac": (traffic / (k_ms_bb * 1e-3) / 1e9 / peak) if traffic else None,
+                                      "how": "%d launches over the %d distinct mini-batches between one event pair, outside "
+                                             "the timed steps" % (bb_reps * N_BATCHES, N_BATCHES)},
                      "note": "frac counts every edge's full source row (SURVEY §8 d); dram_frac counts the bytes DRAM "
                              "actually moved — repeated source rows of a mini-batch are served by L2"},
         "e2e": {"value": e2e_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / args.steps,
