@@ -420,6 +420,7 @@ def extra_partitioned(args, rank, world, dev, barrier):
                "nvlink_bytes_in_per_gpu_per_step": int(t[4].item()),
                "block0_edges_per_step": int(t[5].item()), "block0_dst_rows_per_step": int(t[6].item()),
                "loss": round(r["loss"], 4)}
+        tr.close()
         for p in model.parameters():
             p.grad = None
         barrier()                                            # no peer may still be reading this rank's shard

@@ -258,6 +258,15 @@ class PipelinedSageTrainer:
         return {"time_s": e0.elapsed_time(e1) * 1e-3, "wall_s": time.perf_counter() - t_wall, "n_batches": n,
                 "loss": float(self.loss_sum.item()) / max(n, 1)}
 
+    def close(self):
+        """Drop the captured graphs (they hold the NCCL all-reduce of this trainer's process group).  Call it — or let the
+        trainer be garbage-collected — BEFORE ``dist.destroy_process_group()``: tearing the communicator down while a
+        graph that captured its kernels is still alive blocks (seen with tools/ab_train_priority.py at 2 GPUs)."""
+        self.graphs = None
+        self._prologue = None
+        self._g_train = None
+        torch.cuda.synchronize()
+
     def stage_times(self, seeds, steps=20):
         """Device time of each branch ALONE, replayed as its own CUDA graph (no overlap, no Python dispatch) — the
         numbers behind the ``stage_ms`` of bench.py's partitioned extra.  Trains ``steps`` steps on one mini-batch as a

@@ -37,11 +37,21 @@ for o in range(0, NNZ, 1 << 28):
 lo, hi = P.local_range(rank, N, world)
 table = G.feature_table(hi - lo, F, seed=100 + rank, device=dev)
 labels = torch.randint(0, C, (hi - lo,), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
-per_rank = 256 * BATCH
+per_rank = 128 * BATCH
 seeds = lo + torch.randperm(hi - lo, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))[:per_rank]
 out = {"world": world}
+def log(msg):
+    if rank == 0:
+        print("[ab] " + msg, file=sys.stderr, flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "ab_priority_progress.log"), "a") as f:
+            f.write(msg + "\n")
+
+
+log("setup done")
 for tag, prio in (("default_priorities", False), ("train_branch_high_priority", True), ("default_priorities_again", False),
                   ("train_branch_high_priority_again", True)):
+    log("variant " + tag)
     sharded = P.PeerShardedTable(N, table)
     torch.manual_seed(0)
     model = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
@@ -50,14 +60,19 @@ for tag, prio in (("default_priorities", False), ("train_branch_high_priority", 
                                  precision="tf32", rng_seed=11, label_offset=lo, max_seeds=per_rank, train_priority=prio)
     tr.set_seeds(seeds)
     tr.capture()
+    log("captured")
     tr.epoch(seeds[:16 * BATCH])
+    log("warm epoch done")
     if world > 1:
         dist.barrier()
     r = tr.epoch(seeds)
     t = torch.tensor([r["time_s"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    log("epoch done")
     out[tag] = {"ms_per_step": round(t.item() * 1e3 / r["n_batches"], 4), "loss": round(r["loss"], 4)}
+    log(json.dumps(out))
+    tr.close()
     for p in model.parameters():
         p.grad = None
     if world > 1:
