@@ -37,7 +37,7 @@ enum Opt {
     OPT_GAT_BWD_KERNEL,    // 0 auto, 1 two-pass (CSR then CSR^T), 2 fused single pass over CSR^T
     OPT_GAT_BWD_DEPTH,     // fused backward: gradient rows in flight per lane (4 or 8; 0 = default)
     OPT_BIN_TB,
-    OPT_GEMM_KERNEL,       // 0 auto; see gemm_tcgen05.cu
+    OPT_GEMM_KERNEL,       // 0 auto; 3 = TF32 one-tile-per-CTA kernel, 4 = TF32 persistent kernel, 5 = precision 0 always SIMT FMA
     OPT_NVTX,              // 1 = emit NVTX ranges around the entry points that mirror the reference's ranges
     OPT_COUNT
 };

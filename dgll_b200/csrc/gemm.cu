@@ -13,11 +13,20 @@ extern "C" int dgllb_gemm_f32(const float* A, int64_t lda, int transA, const flo
     DGLLB_REQUIRE(C && (K == 0 || (A && B)), "gemm: null pointer");
     DGLLB_REQUIRE(ldc >= N, "gemm: ldc < N");
     DGLLB_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N), "gemm: leading dimension too small");
-    DGLLB_REQUIRE(precision >= 0 && precision <= 2, "gemm: unknown precision %d", precision);
+    DGLLB_REQUIRE(precision >= 0 && precision <= 3, "gemm: unknown precision %d", precision);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == 3)
+        return gemm_tf32x3(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
     if (precision == 2)
         return gemm_tf32(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
     if (precision == 1)
         return gemm_tcgen05(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
+    // precision 0 = fp32-grade results (north_star's 1e-5 bar).  Products large enough to amortise a persistent launch
+    // run as 3xTF32 on the tensor cores (measured 1-4e-6 of max|ref| against 0.6-1.1e-6 for the FMA kernel, 3-6x faster,
+    // 2x the library's exact-fp32 SGEMM; profiles/r02_gemm_tf32x3.jsonl); small ones and option gemm_kernel=5 take the
+    // exact SIMT FMA kernel.
+    if (opt_get(OPT_GEMM_KERNEL) != 5 && static_cast<double>(M) * static_cast<double>(N) * static_cast<double>(K) >= 2.5e7 &&
+        K >= 32 && N >= 16)
+        return gemm_tf32x3(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
     return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epilogue, accumulate, st);
 }

@@ -277,13 +277,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //     ~400-instruction dependent chain per chunk made the EPILOGUE the bound — 1.85 ms on the K = 100 shape, slower than
 //     the one-tile kernel (ncu: issue active 17 %, tensor pipe 8 %, DRAM 23 %; profiles/r02_gemm_persistent.txt).
 //     C that TMA cannot address (unaligned, or accumulate = read-modify-write) takes the staged LDS/STG path.
-constexpr int kPEpiWarps = 8;
-constexpr int kPThreads = (4 + kPEpiWarps) * 32;
-constexpr int kPStageBytes = kPEpiWarps * 4096;                      // one 32 x 32 fp32 box per epilogue warp
-template <int BNP> struct PersistCfg {
+//
+// X3 = true ("3xTF32", precision 3): fp32-grade results on the tensor cores.  Every fp32 operand word v is split in shared
+// memory into hi = tf32(v) (round to nearest) and lo = v - hi (exact in fp32); the product is accumulated in TMEM as
+// lo*hi + hi*lo + hi*hi — three kind::tf32 MMAs per k-step, the dropped lo*lo term and the tensor core's truncation of lo
+// are ~2^-22 relative.  Four CONVERTER warps sit between the TMA producer and the MMA warp: they wait for a stage to land,
+// rewrite it in place as hi and write lo next to it (an elementwise pass, so the swizzled K-major / MN-major layouts are
+// preserved byte for byte), fence the generic-proxy writes for the async proxy and arrive on the stage's conv barrier,
+// which is what the MMA warp waits for.  Split-K (items = tiles x splits, partial tiles to a workspace, fixed-order
+// reduction) lives in this kernel for X3 so that every shape of a training step takes it.  Four epilogue warps.
+constexpr int kPWarps = 12;
+constexpr int kPThreads = kPWarps * 32;
+constexpr int kPStageBytes = 8 * 4096;                               // one 32 x 32 fp32 box per epilogue warp (<= 8)
+template <int BNP, bool X3> struct PersistCfg {
     static constexpr int stage_b = BNP * BK * 4;
-    static constexpr int stages = (BNP == 256) ? 4 : 6;             // 4 x 48 KB or 6 x 32 KB = 192 KB
-    static constexpr size_t smem = static_cast<size_t>(stages) * (kStageA + stage_b) + kPStageBytes + 1024;
+    static constexpr int stage = (kStageA + stage_b) * (X3 ? 2 : 1);   // X3: [A hi | A lo | B hi | B lo]
+    static constexpr int stages = (192 * 1024) / stage;                 // 4 x 48 KB, 6 x 32 KB, or 3 x 64 KB (X3, BN = 128)
+    static constexpr int epi_warps = X3 ? 4 : 8;
+    static constexpr size_t smem = static_cast<size_t>(stages) * stage + kPStageBytes + 1024;
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
@@ -294,21 +305,24 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <bool A_MN, bool B_MN, int BNP>
+template <bool A_MN, bool B_MN, int BNP, bool X3>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                             const __grid_constant__ CUtensorMap tmap_c, int c_by_tma, float* __restrict__ C,
-                            long long ldc, long long M, int N, int n_tiles_n, long long n_tiles, int num_kb,
-                            const float* __restrict__ bias, int epi, int accumulate) {
-    typedef PersistCfg<BNP> Cfg;
+                            long long ldc, long long M, int N, int n_tiles_n, long long n_tiles, int num_kb_total,
+                            int splits, int kb_per_split, long long slab_rows, const float* __restrict__ bias, int epi,
+                            int accumulate) {
+    typedef PersistCfg<BNP, X3> Cfg;
     constexpr int S = Cfg::stages;
+    constexpr int kEpiWarps = Cfg::epi_warps;
+    constexpr int kStage = Cfg::stage;
+    constexpr int kOffB = X3 ? 2 * kStageA : kStageA;                 // B (hi) inside a stage
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* smem_a = smem;
-    unsigned char* smem_b = smem + S * kStageA;
-    float* stage_c = reinterpret_cast<float*>(smem + S * (kStageA + Cfg::stage_b));   // 1 KB aligned (swizzle atom)
-    __shared__ uint64_t full_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
+    float* stage_c = reinterpret_cast<float*>(smem + S * kStage);                      // 1 KB aligned (swizzle atom)
+    __shared__ uint64_t full_bar[S], conv_bar[S], empty_bar[S], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_holder;
+    const long long n_items = n_tiles * splits;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -319,11 +333,12 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
+            mbar_init(&conv_bar[s], 4);                             // one arrival per converter warp (X3 only)
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], kPEpiWarps);              // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[a], kEpiWarps);               // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -336,7 +351,10 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     if (warp == 0) {
         if (lane == 0) {
             long long it = 0;
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const long long t = w / splits;
+                const int kb0 = static_cast<int>(w - t * splits) * kb_per_split;
+                const int num_kb = min(kb_per_split, num_kb_total - kb0);
                 const int n0 = static_cast<int>(t % n_tiles_n) * BNP;
                 const int m0 = static_cast<int>(t / n_tiles_n) * BM;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -344,9 +362,9 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     mbar_expect_tx(&full_bar[s], kStageA + Cfg::stage_b);
-                    const int k0 = kb * BK;
-                    unsigned char* sa = smem_a + s * kStageA;
-                    unsigned char* sb = smem_b + s * Cfg::stage_b;
+                    const int k0 = (kb0 + kb) * BK;
+                    unsigned char* sa = smem + s * kStage;
+                    unsigned char* sb = sa + kOffB;
                     if (A_MN) {
 #pragma unroll
                         for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &tmap_a, m0 + b * 32, k0, &full_bar[s]);
@@ -368,7 +386,9 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                                    (static_cast<uint32_t>(BNP >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
             long long it = 0;
             int lt = 0;
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            for (long long w = blockIdx.x; w < n_items; w += gridDim.x, ++lt) {
+                const int kb0 = static_cast<int>(w % splits) * kb_per_split;
+                const int num_kb = min(kb_per_split, num_kb_total - kb0);
                 const int as = lt & 1;
                 const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
                 mbar_wait(&tmem_empty_bar[as], aph ^ 1u);           // the epilogue has drained this accumulator
@@ -377,28 +397,47 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = static_cast<int>(it % S);
                     const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
-                    mbar_wait(&full_bar[s], ph);
+                    mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
                     tc_fence_after();
-                    const uint64_t da = A_MN ? make_desc(smem_a + s * kStageA, 4096, 512, 1) : make_desc(smem_a + s * kStageA, 16, 1024, 2);
-                    const uint64_t db = B_MN ? make_desc(smem_b + s * Cfg::stage_b, 4096, 512, 1)
-                                             : make_desc(smem_b + s * Cfg::stage_b, 16, 1024, 2);
+                    unsigned char* sa = smem + s * kStage;
+                    unsigned char* sb = sa + kOffB;
+                    const uint64_t da = A_MN ? make_desc(sa, 4096, 512, 1) : make_desc(sa, 16, 1024, 2);
+                    const uint64_t db = B_MN ? make_desc(sb, 4096, 512, 1) : make_desc(sb, 16, 1024, 2);
+                    if (X3) {
+                        const uint64_t da_lo = A_MN ? make_desc(sa + kStageA, 4096, 512, 1) : make_desc(sa + kStageA, 16, 1024, 2);
+                        const uint64_t db_lo = B_MN ? make_desc(sb + Cfg::stage_b, 4096, 512, 1)
+                                                    : make_desc(sb + Cfg::stage_b, 16, 1024, 2);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)
-                        tc_mma_tf32(tmem_d, da + static_cast<uint64_t>((A_MN ? 64 : 2) * k),
-                                    db + static_cast<uint64_t>((B_MN ? 64 : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint64_t oa = static_cast<uint64_t>((A_MN ? 64 : 2) * k), ob = static_cast<uint64_t>((B_MN ? 64 : 2) * k);
+                            tc_mma_tf32(tmem_d, da_lo + oa, db + ob, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+                            tc_mma_tf32(tmem_d, da + oa, db_lo + ob, idesc, 1u);
+                            tc_mma_tf32(tmem_d, da + oa, db + ob, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k)
+                            tc_mma_tf32(tmem_d, da + static_cast<uint64_t>((A_MN ? 64 : 2) * k),
+                                        db + static_cast<uint64_t>((B_MN ? 64 : 2) * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     tc_commit(&empty_bar[s]);
                 }
                 tc_commit(&tmem_full_bar[as]);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + kEpiWarps) {
         const int ew = warp - 4;
         const int q = ew & 3;                                       // TMEM lane quarter this warp may read (= warp % 4)
-        const int half = ew >> 2;                                   // it takes the chunks c = half, half + 2, ...
+        const int half = ew >> 2;                                   // it takes the chunks c = half, half + kStep, ...
+        constexpr int kStep = kEpiWarps / 4;
         float* tile = stage_c + ew * 1024;
         const int sw = lane & 7;                                    // swizzle term of this lane's staged row
         int lt = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+        float* const C0 = C;
+        for (long long w = blockIdx.x; w < n_items; w += gridDim.x, ++lt) {
+            const long long t = w / splits;
+            const long long zrow = (w - t * splits) * slab_rows;    // split z writes rows [z*slab_rows, ...) of the workspace
+            C = C0 + zrow * ldc;
             const int as = lt & 1;
             const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
             const int n0 = static_cast<int>(t % n_tiles_n) * BNP;
@@ -411,11 +450,11 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             if (n_chunks > NC) n_chunks = NC;
             bool released = false;
 #pragma unroll 1
-            for (int c = half; c < n_chunks; c += 2) {
+            for (int c = half; c < n_chunks; c += kStep) {
                 const int cbase = n0 + c * 32;
                 uint32_t r[32];
                 tmem_ld32(tacc + static_cast<uint32_t>(c * 32), r);
-                if (c + 2 >= n_chunks) {                            // this warp's part of the accumulator is read out
+                if (c + kStep >= n_chunks) {                        // this warp's part of the accumulator is read out
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
@@ -439,7 +478,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0 && row0 < M) tma_store_2d(&tmap_c, tile, cbase, static_cast<int>(row0));
+                    if (lane == 0 && row0 < M) tma_store_2d(&tmap_c, tile, cbase, static_cast<int>(zrow + row0));
                 } else {
                     const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && cbase + 32 <= N;
                     if (vec_ok) {
@@ -497,6 +536,48 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             }
         }
         if (c_by_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    } else if (X3 && warp >= 8) {
+        // converters: 128 threads rewrite a landed stage as (hi, lo); thread t takes the 16-byte vectors t, t + 128, ...
+        const int ct = threadIdx.x - 8 * 32;
+        long long it = 0;
+        for (long long w = blockIdx.x; w < n_items; w += gridDim.x) {
+            const int kb0 = static_cast<int>(w % splits) * kb_per_split;
+            const int num_kb = min(kb_per_split, num_kb_total - kb0);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = static_cast<int>(it % S);
+                const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                unsigned char* sa = smem + s * kStage;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    float4* hi = reinterpret_cast<float4*>(part == 0 ? sa : sa + kOffB);
+                    constexpr int nA = kStageA / 16, nB = Cfg::stage_b / 16;
+                    const int nv = part == 0 ? nA : nB;
+                    float4* lo = hi + nv;
+#pragma unroll 4
+                    for (int i = ct; i < nv; i += 128) {
+                        const float4 v = hi[i];
+                        float4 h, l;
+                        uint32_t u;
+                        // hi = rn_tf32(v); lo = rn_tf32(v - hi): lo is rounded HERE (to nearest) because the tensor core
+                        // would truncate it — a bias that grows linearly with K (first version: 4.3e-6 at K = 602)
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x - h.x)); l.x = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y - h.y)); l.y = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z - h.z)); l.z = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w - h.w)); l.w = __uint_as_float(u);
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&conv_bar[s])) : "memory");
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -591,41 +672,53 @@ static void launch(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& t
                                                                bias, epi, accumulate);
 }
 
-template <bool A_MN, bool B_MN, int BNP>
-static cudaError_t launch_persistent(int grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb,
-                                     const CUtensorMap& tc, int c_by_tma, float* C, long long ldc, long long M, int N, int n_tiles_n, long long n_tiles, int num_kb,
-                                     const float* bias, int epi, int accumulate) {
+struct PersistArgs {
+    int grid;
+    cudaStream_t st;
+    CUtensorMap ta, tb, tc;
+    int c_by_tma;
+    float* C;
+    long long ldc, M;
+    int N, n_tiles_n;
+    long long n_tiles;
+    int num_kb, splits, kb_per;
+    long long slab_rows;
+    const float* bias;
+    int epi, accumulate;
+};
+
+template <bool A_MN, bool B_MN, int BNP, bool X3>
+static cudaError_t launch_persistent(const PersistArgs& a) {
     static std::once_flag once[64];
     static cudaError_t err[64];
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     const int slot = dev_id & 63;
     std::call_once(once[slot], [&]() {
-        err[slot] = cudaFuncSetAttribute(gemm_tf32_persistent_kernel<A_MN, B_MN, BNP>,
+        err[slot] = cudaFuncSetAttribute(gemm_tf32_persistent_kernel<A_MN, B_MN, BNP, X3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(PersistCfg<BNP>::smem));
+                                         static_cast<int>(PersistCfg<BNP, X3>::smem));
     });
     if (err[slot] != cudaSuccess) return err[slot];
-    gemm_tf32_persistent_kernel<A_MN, B_MN, BNP><<<grid, kPThreads, PersistCfg<BNP>::smem, st>>>(
-        ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+    gemm_tf32_persistent_kernel<A_MN, B_MN, BNP, X3><<<a.grid, kPThreads, PersistCfg<BNP, X3>::smem, a.st>>>(
+        a.ta, a.tb, a.tc, a.c_by_tma, a.C, a.ldc, a.M, a.N, a.n_tiles_n, a.n_tiles, a.num_kb, a.splits, a.kb_per,
+        a.slab_rows, a.bias, a.epi, a.accumulate);
     return cudaSuccess;
 }
 
-template <int BNP>
-static cudaError_t launch_persistent_mn(bool a_mn, bool b_mn, int grid, cudaStream_t st, const CUtensorMap& ta,
-                                        const CUtensorMap& tb, const CUtensorMap& tc, int c_by_tma, float* C, long long ldc, long long M, int N, int n_tiles_n,
-                                        long long n_tiles, int num_kb, const float* bias, int epi, int accumulate) {
-    if (a_mn && b_mn) return launch_persistent<true, true, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
-    if (a_mn) return launch_persistent<true, false, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
-    if (b_mn) return launch_persistent<false, true, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
-    return launch_persistent<false, false, BNP>(grid, st, ta, tb, tc, c_by_tma, C, ldc, M, N, n_tiles_n, n_tiles, num_kb, bias, epi, accumulate);
+template <int BNP, bool X3>
+static cudaError_t launch_persistent_mn(bool a_mn, bool b_mn, const PersistArgs& a) {
+    if (a_mn && b_mn) return launch_persistent<true, true, BNP, X3>(a);
+    if (a_mn) return launch_persistent<true, false, BNP, X3>(a);
+    if (b_mn) return launch_persistent<false, true, BNP, X3>(a);
+    return launch_persistent<false, false, BNP, X3>(a);
 }
 
 }  // namespace tf32
 
-int gemm_tf32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
-              long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
-              cudaStream_t st) {
+static int gemm_tf32_impl(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                          long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
+                          bool x3, cudaStream_t st) {
     using namespace tf32;
     if (K == 0 || N >= (1ll << 31) || K >= (1ll << 30) || M >= (1ll << 31)) {
         return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epi, accumulate, st);
@@ -676,30 +769,68 @@ int gemm_tf32(const float* A, long long lda, int transA, const float* B, long lo
         CUtensorMap ta, tb;
         const CUtensorMapSwizzle sw_k = CU_TENSOR_MAP_SWIZZLE_128B, sw_mn = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
         if ((rc = a_mn ? make_tmap(&ta, A, M, K, lda, 32, BK, sw_mn) : make_tmap(&ta, A, K, M, lda, BK, BM, sw_k)) != DGLLB_OK) break;
-        // persistent kernel (one CTA per SM, BN = 256 when N > 128, two accumulators): at least one tile per SM
+        // persistent kernel (one CTA per SM, two accumulators): TF32 when there is at least one tile per SM; 3xTF32 always
+        // (with its own split-K for the long-reduction / few-tile shapes)
         {
             // BN = 256 reads A once per row block, but pads N to a multiple of 256: keep it only while that costs < 10 %
-            // more columns than 128-wide tiles would (N = 602: 768 vs 640 columns -> 128)
+            // more columns than 128-wide tiles would (N = 602: 768 vs 640 columns -> 128).  3xTF32 stages hold hi and lo
+            // of both operands: BN = 128 (3 stages of 64 KB).
             const long long pad256 = (N + 255) / 256 * 256, pad128 = (N + 127) / 128 * 128;
-            const int bnp = (N > 128 && pad256 * 10 <= pad128 * 11) ? 256 : 128;
+            const int bnp = (!x3 && N > 128 && pad256 * 10 <= pad128 * 11) ? 256 : 128;
             const long long p_tiles_m = (M + BM - 1) / BM;
             const int p_tiles_n = static_cast<int>((N + bnp - 1) / bnp);
             const long long p_tiles = p_tiles_m * p_tiles_n;
             const int gk = opt_get(OPT_GEMM_KERNEL);   // 3 pins the one-tile-per-CTA kernel, 4 the persistent one
-            if ((p_tiles >= di.sm_count || gk == 4) && gk != 3 && p_tiles_m < (1ll << 24)) {
+            if (x3 || ((p_tiles >= di.sm_count || gk == 4) && gk != 3 && p_tiles_m < (1ll << 24))) {
+                if (p_tiles_m >= (1ll << 24)) { rc = DGLLB_ERR_UNSUPPORTED; set_error("gemm: too many row blocks"); break; }
                 if ((rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 32, BK, sw_mn) : make_tmap(&tb, B, K, N, ldb, BK, bnp, sw_k)) != DGLLB_OK) break;
-                const int grid_p = static_cast<int>(p_tiles < di.sm_count ? p_tiles : di.sm_count);
-                const int nkb = static_cast<int>((K + BK - 1) / BK);
+                PersistArgs pa;
+                pa.st = st; pa.ta = ta; pa.tb = tb; pa.tc = ta;
+                pa.M = M; pa.N = static_cast<int>(N); pa.n_tiles_n = p_tiles_n; pa.n_tiles = p_tiles;
+                pa.num_kb = static_cast<int>((K + BK - 1) / BK);
+                pa.splits = 1; pa.kb_per = pa.num_kb; pa.slab_rows = 0;
+                pa.C = C; pa.ldc = ldc; pa.bias = bias; pa.epi = epi; pa.accumulate = accumulate;
+                if (x3 && p_tiles * 2 <= di.sm_count && pa.num_kb >= 16) {      // deterministic split-K, as the one-tile kernel
+                    long long want = di.sm_count / p_tiles;
+                    if (want > 32) want = 32;
+                    if (want > pa.num_kb / 8) want = pa.num_kb / 8;
+                    if (want >= 2) {
+                        pa.kb_per = static_cast<int>((pa.num_kb + want - 1) / want);
+                        pa.splits = (pa.num_kb + pa.kb_per - 1) / pa.kb_per;
+                    }
+                }
+                long long ldp = 0;
+                if (pa.splits > 1) {
+                    ldp = (N + 3) / 4 * 4;
+                    pa.slab_rows = p_tiles_m * BM;                             // whole row blocks: a slab never spills into the next
+                    cudaError_t e = cudaMallocAsync(&part, sizeof(float) * static_cast<size_t>(pa.slab_rows) * ldp * pa.splits, st);
+                    if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
+                    pa.C = part; pa.ldc = ldp; pa.bias = nullptr; pa.epi = 0; pa.accumulate = 0;
+                }
                 // C goes out by TMA store when the tensor map can address it and nothing has to be read back
-                CUtensorMap tc = ta;
-                const int c_by_tma = (tma_ok(C, ldc) && !accumulate) ? 1 : 0;
-                if (c_by_tma && (rc = make_tmap(&tc, C, N, M, ldc, 32, 32, sw_k)) != DGLLB_OK) break;
-                cudaError_t e = bnp == 256
-                    ? launch_persistent_mn<256>(a_mn, b_mn, grid_p, st, ta, tb, tc, c_by_tma, C, ldc, M, static_cast<int>(N), p_tiles_n, p_tiles, nkb, bias, epi, accumulate)
-                    : launch_persistent_mn<128>(a_mn, b_mn, grid_p, st, ta, tb, tc, c_by_tma, C, ldc, M, static_cast<int>(N), p_tiles_n, p_tiles, nkb, bias, epi, accumulate);
+                pa.c_by_tma = (tma_ok(pa.C, pa.ldc) && !pa.accumulate) ? 1 : 0;
+                if (pa.c_by_tma) {
+                    const long long c_rows = pa.splits > 1 ? pa.slab_rows * pa.splits : M;
+                    if ((rc = make_tmap(&pa.tc, pa.C, N, c_rows, pa.ldc, 32, 32, sw_k)) != DGLLB_OK) break;
+                }
+                const long long items = p_tiles * pa.splits;
+                pa.grid = static_cast<int>(items < di.sm_count ? items : di.sm_count);
+                cudaError_t e = x3 ? launch_persistent_mn<128, true>(a_mn, b_mn, pa)
+                              : bnp == 256 ? launch_persistent_mn<256, false>(a_mn, b_mn, pa)
+                                           : launch_persistent_mn<128, false>(a_mn, b_mn, pa);
                 if (e == cudaSuccess) e = cudaGetLastError();
-                if (e != cudaSuccess) { set_error("gemm: persistent launch failed: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
+                if (e != cudaSuccess) { set_error("gemm: persistent launch failed: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; break; }
                 g_launch_count.fetch_add(1);
+                if (pa.splits > 1) {
+                    long long rb = (M * N + 255) / 256;
+                    if (rb > static_cast<long long>(di.sm_count) * 8) rb = static_cast<long long>(di.sm_count) * 8;
+                    splitk_reduce_kernel<<<static_cast<unsigned>(rb), 256, 0, st>>>(part, pa.slab_rows * ldp, pa.splits, C, ldc, M,
+                                                                                    static_cast<int>(N), static_cast<int>(ldp),
+                                                                                    bias, epi, accumulate);
+                    g_launch_count.fetch_add(1);
+                    e = cudaGetLastError();
+                    if (e != cudaSuccess) { set_error("gemm: %s", cudaGetErrorString(e)); rc = DGLLB_ERR_CUDA; }
+                }
                 break;
             }
         }
@@ -769,6 +900,18 @@ int gemm_tf32(const float* A, long long lda, int transA, const float* B, long lo
     if (part) cudaFreeAsync(part, st);
     if (ws) cudaFreeAsync(ws, st);
     return rc;
+}
+
+int gemm_tf32(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+              long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
+              cudaStream_t st) {
+    return gemm_tf32_impl(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epi, accumulate, false, st);
+}
+
+int gemm_tf32x3(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
+                cudaStream_t st) {
+    return gemm_tf32_impl(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, epi, accumulate, true, st);
 }
 
 }  // namespace dgllb

@@ -66,4 +66,10 @@ int gemm_tf32(const float* A, long long lda, int transA, const float* B, long lo
               long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
               cudaStream_t st);
 
+// 3xTF32: every fp32 operand word split into tf32 hi + lo in shared memory, three MMAs per k-step: fp32-grade results
+// (~1e-6 of max|ref|) on the tensor cores (gemm_tf32.cu)
+int gemm_tf32x3(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                long long ldc, long long M, long long N, long long K, const float* bias, int epi, int accumulate,
+                cudaStream_t st);
+
 }  // namespace dgllb

@@ -299,7 +299,8 @@ def ipc_release(ptr, offset):
 def gemm(a, b, bias=None, relu=False, elu=False, trans_a=False, trans_b=False, out=None, accumulate=False,
          precision="fp32"):
     """Dense transform ``op(a) @ op(b) (+bias)``: ``fp32`` = exact SIMT path, ``bf16`` = tcgen05 on packed bf16 operands,
-    ``tf32`` = tcgen05 on the fp32 operands as they lie in memory (TMA, no packing)."""
+    ``tf32`` = tcgen05 on the fp32 operands as they lie in memory (TMA, no packing), ``tf32x3`` = the same kernel with
+    every operand word split into tf32 hi + lo in shared memory and three MMAs per k-step (fp32-grade results)."""
     _need_cuda(a, b, bias, out)
     a, lda = _rowmajor(a.to(torch.float32), "a")
     b, ldb = _rowmajor(b.to(torch.float32), "b")
@@ -319,7 +320,7 @@ def gemm(a, b, bias=None, relu=False, elu=False, trans_a=False, trans_b=False, o
     if bias is not None:
         bias = bias.to(torch.float32).contiguous()
     epi = (EPI_RELU if relu else 0) | (EPI_ELU if elu else 0)
-    prec = {"fp32": 0, "bf16": 1, "tf32": 2}[precision]
+    prec = {"fp32": 0, "bf16": 1, "tf32": 2, "tf32x3": 3}[precision]
     check(lib().dgllb_gemm_f32(_p(a), lda, int(trans_a), _p(b), ldb, int(trans_b), _p(out), ldc, M, N, K,
                                _p(bias), epi, int(accumulate), prec, _stream()), "gemm")
     return out

@@ -22,8 +22,8 @@ _PRECISION = {"gemm": "fp32"}
 def set_gemm_precision(p):
     """'fp32' = exact SIMT fp32 FMA (parity path, <=1e-5); 'tf32' = tcgen05 tensor cores reading the fp32 operands in
     place (TF32, fp32 accumulation in TMEM, <=2e-3); 'bf16' = tcgen05 on operands packed to bf16 (<=1e-2)."""
-    if p not in ("fp32", "bf16", "tf32"):
-        raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
+    if p not in ("fp32", "bf16", "tf32", "tf32x3"):
+        raise ValueError("precision must be 'fp32', 'tf32x3', 'tf32' or 'bf16'")
     _PRECISION["gemm"] = p
 
 

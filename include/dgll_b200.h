@@ -238,12 +238,16 @@ int dgllb_ipc_release(void* dev_ptr, int64_t offset);
 
 /*
  * C[M,N] = epi( A[M,K] . B[K,N] + bias[N] ), all row-major fp32 in HBM.
- * precision 0: exact fp32 FMA (SIMT) — the parity path (<=1e-5 rel);
+ * precision 0: fp32-grade results, the parity path (<=1e-5 rel): products of >= 2.5e7 multiply-adds run as precision 3,
+ *              smaller ones (and every one under option gemm_kernel=5) on the exact fp32 FMA kernel (SIMT);
  * precision 1: tcgen05 tensor cores, bf16 operands (packed by a pre-pass),
  *              fp32 accumulate in TMEM (<=1e-2 rel); the faster choice for large square products;
  * precision 2: tcgen05 tensor cores, TF32 operands read by TMA straight from the fp32 tensors (no packing, no
  *              transposition: operands stored the other way round are loaded MN-major), fp32 accumulate in TMEM
  *              (<=2e-3 rel) — the fast path for the layer shapes of this path, which are bound by HBM traffic.
+ * precision 3: "3xTF32" — the precision-2 kernel with every fp32 operand word split in shared memory into
+ *              hi = tf32(v) and lo = tf32(v - hi) and three MMAs per k-step (lo*hi + hi*lo + hi*hi), fp32
+ *              accumulation in TMEM: 1-4e-6 of max|ref|, deterministic (fixed-order split-K).
  * transA / transB: use A^T (A stored [K,M]) / B^T (B stored [N,K]).
  * Replaces torch.mm(x, W) gcnconv.py:30, gcn_model.py:70, gatconv.py:117 and the
  * per-edge recomputed transform of gcn_fused_kernel.cu:46-54.

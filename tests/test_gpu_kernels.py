@@ -825,6 +825,36 @@ def test_gemm_tf32_persistent_kernel(K, M, N, K_):
     assert torch.equal(K.gemm(da, db, precision="tf32"), outs[0]) or K_ >= 512
 
 
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (300, 64, 50), (1000, 256, 602), (17, 5, 3), (129, 130, 65),
+                                    (4096, 300, 256), (40000, 256, 100), (602, 256, 11264), (257, 300, 4096)])
+def test_gemm_tf32x3_fp32_grade(K, M, N, K_):
+    """precision='tf32x3': operands split into tf32 hi + lo inside the kernel, three MMAs per k-step, fp32 accumulation in
+    TMEM.  Bar: the fp32 bar of north_star (1e-5 of max|ref| against the fp64 product) — measured ~1e-6 — in all four
+    operand orientations, with epilogue / accumulate / ragged edges, and through the kernel's own split-K on the
+    long-reduction shapes; deterministic."""
+    rng = np.random.default_rng(M + 7 * N)
+    a = rng.standard_normal((M, K_)).astype(np.float32)
+    b = rng.standard_normal((K_, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    da, db = dev(a), dev(b)
+    at, bt = da.t().contiguous(), db.t().contiguous()
+    outs = [K.gemm(da, db, precision="tf32x3"), K.gemm(at, db, trans_a=True, precision="tf32x3"),
+            K.gemm(da, bt, trans_b=True, precision="tf32x3"),
+            K.gemm(at, bt, trans_a=True, trans_b=True, precision="tf32x3")]
+    for o in outs:
+        assert rel_err(o.cpu().numpy(), ref) <= FP32_TOL
+        assert torch.equal(o, outs[0])
+    assert rel_err(outs[0].cpu().numpy(), ref) <= 4 * rel_err(K.gemm(da, db, precision="fp32").cpu().numpy(), ref) + 2e-6
+    out = K.gemm(da, db, bias=dev(bias), relu=True, precision="tf32x3").cpu().numpy()
+    assert rel_err(out, np.maximum(ref + bias, 0)) <= FP32_TOL
+    acc = rng.standard_normal((M, N)).astype(np.float32)
+    o = dev(acc)
+    K.gemm(da, db, out=o, accumulate=True, precision="tf32x3")
+    assert rel_err(o.cpu().numpy(), acc + ref) <= FP32_TOL
+    assert torch.equal(K.gemm(da, db, precision="tf32x3"), outs[0])
+
+
 def test_layers_run_on_the_tf32_path():
     import dgll_b200.nn as nn
     from dgll_b200 import ops

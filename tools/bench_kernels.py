@@ -154,13 +154,21 @@ def main():
                 d.update(extra or {})
                 print(json.dumps(d), flush=True)
 
-            for prec in ("tf32", "bf16", "fp32"):
+            ref64 = None
+            if M * Kd * Nd <= 2e10:
+                ref64 = a.double() @ w.double().t()
+            for prec in ("tf32", "tf32x3", "bf16", "fp32"):
                 if prec == "fp32" and M * Kd * Nd > 4e11:
                     continue
                 ms = timeit(lambda: K.gemm(a, w, out=out, trans_b=True, precision=prec), args.iters)
-                rep("gemm fwd x@W^T [%s]" % {"tf32": "tcgen05 tf32, TMA on fp32", "bf16": "tcgen05 bf16 + pack", "fp32": "simt fp32"}[prec], ms)
+                extra = None
+                if ref64 is not None:
+                    extra = {"max_err_over_max_ref": float((out.double() - ref64).abs().max() / ref64.abs().max())}
+                rep("gemm fwd x@W^T [%s]" % {"tf32": "tcgen05 tf32, TMA on fp32", "tf32x3": "tcgen05 3xTF32 (hi/lo split in smem)",
+                                              "bf16": "tcgen05 bf16 + pack", "fp32": "simt fp32"}[prec], ms, extra)
+            del ref64
             if M * Kd * Nd <= 4e11:
-                for prec in ("tf32", "bf16"):
+                for prec in ("tf32", "tf32x3", "bf16"):
                     dw = torch.empty((Nd, Kd), device=dev)
                     ms = timeit(lambda: K.gemm(go, a, trans_a=True, out=dw, precision=prec), args.iters)
                     rep("gemm dW = G^T X [%s]" % prec, ms)
@@ -176,6 +184,8 @@ def main():
             ms = timeit(lambda: torch.matmul(ac, wc.t(), out=out), args.iters)
             rep("torch.matmul fp32 operands, TF32 allowed (cuBLAS comparator, same I/O as ours)", ms)
             torch.backends.cuda.matmul.allow_tf32 = False
+            ms = timeit(lambda: torch.matmul(ac, wc.t(), out=out), args.iters)
+            rep("torch.matmul fp32 operands, exact fp32 (cuBLAS SGEMM comparator for fp32 / 3xTF32)", ms)
             del a, w, go, out, ab, wb, ac, wc
 
     if "gat" in which:
