@@ -342,7 +342,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc(&tmem_base_holder, 2 * BNP);
+    constexpr int kAccCols = X3 ? 2 * BNP : BNP;                      // X3: two accumulators per stage, k-blocks alternate
+    if (warp == 2) tmem_alloc(&tmem_base_holder, 2 * kAccCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -393,8 +394,14 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 const uint32_t aph = static_cast<uint32_t>(lt >> 1) & 1u;
                 mbar_wait(&tmem_empty_bar[as], aph ^ 1u);           // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BNP);
+                const uint32_t tmem_d0 = tmem_base + static_cast<uint32_t>(as * kAccCols);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    // The tensor core's fp32 accumulation truncates: a chain of n accumulating MMAs comes out low by about
+                    // n * 2^-24 of its magnitude (measured: 4.4e-6 of max|ref| at K = 602 with one accumulator = 76 k-steps).
+                    // X3 alternates two accumulators per k-block — two chains of half the length, added with
+                    // round-to-nearest in the epilogue — and the host caps the k-blocks of one item.
+                    const uint32_t tmem_d = X3 ? tmem_d0 + static_cast<uint32_t>((kb & 1) * BNP) : tmem_d0;
+                    const int kb_first = X3 ? (kb >> 1) : kb;        // 0 on the first k-block that touches this accumulator
                     const int s = static_cast<int>(it % S);
                     const uint32_t ph = static_cast<uint32_t>(it / S) & 1u;
                     mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
@@ -410,7 +417,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
                             const uint64_t oa = static_cast<uint64_t>((A_MN ? 64 : 2) * k), ob = static_cast<uint64_t>((B_MN ? 64 : 2) * k);
-                            tc_mma_tf32(tmem_d, da_lo + oa, db + ob, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+                            tc_mma_tf32(tmem_d, da_lo + oa, db + ob, idesc, (kb_first | k) != 0 ? 1u : 0u);   // small terms first
                             tc_mma_tf32(tmem_d, da + oa, db_lo + ob, idesc, 1u);
                             tc_mma_tf32(tmem_d, da + oa, db + ob, idesc, 1u);
                         }
@@ -444,7 +451,9 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             const long long row0 = (t / n_tiles_n) * BM + q * 32;
             mbar_wait(&tmem_full_bar[as], aph);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + static_cast<uint32_t>(as * BNP) + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t tacc = tmem_base + static_cast<uint32_t>(as * kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
+            const int kb0_e = static_cast<int>(w - t * splits) * kb_per_split;
+            const bool two_acc = X3 && min(kb_per_split, num_kb_total - kb0_e) > 1;   // the second accumulator was written
             constexpr int NC = BNP / 32;
             int n_chunks = (N - n0 + 31) / 32;
             if (n_chunks > NC) n_chunks = NC;
@@ -454,6 +463,12 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 const int cbase = n0 + c * 32;
                 uint32_t r[32];
                 tmem_ld32(tacc + static_cast<uint32_t>(c * 32), r);
+                if (two_acc) {
+                    uint32_t r2[32];
+                    tmem_ld32(tacc + static_cast<uint32_t>(BNP + c * 32), r2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                }
                 if (c + kStep >= n_chunks) {                        // this warp's part of the accumulator is read out
                     tc_fence_before();
                     __syncwarp();
@@ -581,7 +596,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 2 * BNP);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * kAccCols);
 }
 
 // dst[r, 0:cols] = src[r, 0:cols], dst row stride ldd (a multiple of 4 floats), pad columns zero
@@ -794,6 +809,13 @@ static int gemm_tf32_impl(const float* A, long long lda, int transA, const float
                     long long want = di.sm_count / p_tiles;
                     if (want > 32) want = 32;
                     if (want > pa.num_kb / 8) want = pa.num_kb / 8;
+                    // the tensor core's fp32 accumulation truncates (see the MMA warp): one item accumulates at most 16 k-blocks
+                    // (two chains of 32 k-steps), the partial tiles are summed with round-to-nearest by the reduction kernel
+                    // (dW = X^T G over 233 K rows: 455 splits, 300 MB of partial tiles)
+                    long long need = (pa.num_kb + 15) / 16;
+                    const long long ws_cap = (1ll << 30) / (p_tiles * BM * bnp * 4);   // at most ~1 GB of partial tiles
+                    if (need > ws_cap) need = ws_cap;
+                    if (want < need) want = need;
                     if (want >= 2) {
                         pa.kb_per = static_cast<int>((pa.num_kb + want - 1) / want);
                         pa.splits = (pa.num_kb + pa.kb_per - 1) / pa.kb_per;

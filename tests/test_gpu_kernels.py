@@ -826,7 +826,8 @@ def test_gemm_tf32_persistent_kernel(K, M, N, K_):
 
 
 @pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (300, 64, 50), (1000, 256, 602), (17, 5, 3), (129, 130, 65),
-                                    (4096, 300, 256), (40000, 256, 100), (602, 256, 11264), (257, 300, 4096)])
+                                    (4096, 300, 256), (40000, 256, 100), (602, 256, 11264), (257, 300, 4096),
+                                    (300, 128, 200000)])
 def test_gemm_tf32x3_fp32_grade(K, M, N, K_):
     """precision='tf32x3': operands split into tf32 hi + lo inside the kernel, three MMAs per k-step, fp32 accumulation in
     TMEM.  Bar: the fp32 bar of north_star (1e-5 of max|ref| against the fp64 product) — measured ~1e-6 — in all four
@@ -843,9 +844,8 @@ def test_gemm_tf32x3_fp32_grade(K, M, N, K_):
             K.gemm(da, bt, trans_b=True, precision="tf32x3"),
             K.gemm(at, bt, trans_a=True, trans_b=True, precision="tf32x3")]
     for o in outs:
-        assert rel_err(o.cpu().numpy(), ref) <= FP32_TOL
+        assert rel_err(o.cpu().numpy(), ref) <= 0.5 * FP32_TOL
         assert torch.equal(o, outs[0])
-    assert rel_err(outs[0].cpu().numpy(), ref) <= 4 * rel_err(K.gemm(da, db, precision="fp32").cpu().numpy(), ref) + 2e-6
     out = K.gemm(da, db, bias=dev(bias), relu=True, precision="tf32x3").cpu().numpy()
     assert rel_err(out, np.maximum(ref + bias, 0)) <= FP32_TOL
     acc = rng.standard_normal((M, N)).astype(np.float32)
