@@ -32,6 +32,7 @@ enum Opt {
     OPT_SPMM_TB,           // rowsplit kernel block size
     OPT_ROWS_TB, OPT_ROWS_NS, OPT_ROWS_D,   // whole-row kernel: block size, slabs per warp, window depth
     OPT_ROWS_STREAM,       // whole-row kernel across rows: 0 auto, 1 off, n >= 2 = n rows per warp
+    OPT_ROWS_SHARDED_BPS,  // sharded aggregation: resident 64-thread blocks per SM (5..16; 0 = no limit)
     OPT_GAT_KERNEL,        // 0 auto, 1 generic (lane-group), 2 whole-row
     OPT_GAT_ROW_WARPS, OPT_GAT_BWD_TB,
     OPT_GAT_BWD_KERNEL,    // 0 auto, 1 two-pass (CSR then CSR^T), 2 fused single pass over CSR^T

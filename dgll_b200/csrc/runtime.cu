@@ -68,6 +68,7 @@ static const OptDesc kOpts[OPT_COUNT] = {
     {"rows_ns", "DGLLB_ROWS_NS", nullptr},
     {"rows_d", "DGLLB_ROWS_D", nullptr},
     {"rows_stream", "DGLLB_ROWS_STREAM", nullptr},
+    {"rows_sharded_bps", "DGLLB_ROWS_SHARDED_BPS", nullptr},
     {"gat_kernel", "DGLLB_GAT_KERNEL", kGatWords},
     {"gat_row_warps", "DGLLB_GAT_ROW_WARPS", nullptr},
     {"gat_bwd_tb", "DGLLB_GAT_BWD_TB", nullptr},

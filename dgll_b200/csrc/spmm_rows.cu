@@ -379,8 +379,22 @@ static int stream_rows_per_warp(long long n_dst, int n_pass, int sm_count, int r
     return static_cast<int>(r);
 }
 
+// The sharded aggregation runs on a graph branch BESIDE the training step; its warps sit on NVLink round trips (~2,000
+// cycles) while holding registers, and at full residency they take ~94 % of the register file, so the training branch's
+// CTAs cannot start on an SM until it drains.  Option rows_sharded_bps = n caps the resident 64-thread blocks per SM at n
+// by asking for 1/n of the shared memory the kernel never touches (NVLink needs ~2 MB in flight per GPU: 10 warps per SM
+// with an 8-deep window hold 6 MB).
+static size_t sharded_throttle_smem(bool sharded) {
+    if (!sharded) return 0;
+    const int bps = opt_get(OPT_ROWS_SHARDED_BPS);
+    if (bps < 5 || bps > 16) return 0;
+    size_t b = (static_cast<size_t>(227) * 1024 / bps - 1024) & ~static_cast<size_t>(1023);
+    return b > 48 * 1024 ? 48 * 1024 : b;
+}
+
 template <typename XT, int NS, int D, bool HAS_VALS, bool SHARDED>
 static int rows_launch(const RowsParams& p, int tb, cudaStream_t st) {
+    const size_t thr_smem = sharded_throttle_smem(SHARDED);
     constexpr int DS = (D >= 8) ? 8 : (D >= 3 ? 4 : 2);                       // streaming depth must divide 32
     const bool plain = !p.row_scale && !p.addend && !p.bias && !p.epi;
     // bf16 rows: the streaming variant measured slower than the per-row kernel (70.5 vs 78.3 us) — fp32 only
@@ -394,12 +408,14 @@ static int rows_launch(const RowsParams& p, int tb, cudaStream_t st) {
                 nb = 8;
             return nb * 2;
         }();
-        const int R = stream_rows_per_warp(p.n_dst, p.n_pass, di.sm_count, resident);
+        int res_eff = resident;
+        if (thr_smem) { const int cap = opt_get(OPT_ROWS_SHARDED_BPS) * 2; if (cap < res_eff) res_eff = cap; }
+        const int R = stream_rows_per_warp(p.n_dst, p.n_pass, di.sm_count, res_eff);
         if (R >= 2) {
             const long long warps = (p.n_dst + R - 1) / R * p.n_pass;
             const long long blocks = (warps + 1) / 2;
             DGLLB_REQUIRE(blocks < (1ll << 31), "spmm_rows: grid too large (%lld blocks)", blocks);
-            spmm_rows_stream_kernel<XT, NS, DS, HAS_VALS, SHARDED><<<static_cast<unsigned>(blocks), 64, 0, st>>>(p, R);
+            spmm_rows_stream_kernel<XT, NS, DS, HAS_VALS, SHARDED><<<static_cast<unsigned>(blocks), 64, thr_smem, st>>>(p, R);
             DGLLB_LAUNCH_CHECK();
             return DGLLB_OK;
         }
@@ -407,7 +423,7 @@ static int rows_launch(const RowsParams& p, int tb, cudaStream_t st) {
     const long long warps = p.n_dst * p.n_pass;
     const long long blocks = (warps * 32 + tb - 1) / tb;
     DGLLB_REQUIRE(blocks < (1ll << 31), "spmm_rows: grid too large (%lld blocks)", blocks);
-    spmm_rows_kernel<XT, NS, D, HAS_VALS, SHARDED><<<static_cast<unsigned>(blocks), tb, 0, st>>>(p);
+    spmm_rows_kernel<XT, NS, D, HAS_VALS, SHARDED><<<static_cast<unsigned>(blocks), tb, thr_smem, st>>>(p);
     DGLLB_LAUNCH_CHECK();
     return DGLLB_OK;
 }

@@ -73,7 +73,7 @@ class PipelinedSageTrainer:
 
     def __init__(self, model, opt, labels, row_ptr, col_idx, n_feat, table=None, sharded=None, batch_size=1024,
                  fanouts=(25, 10), group=None, precision=None, rng_seed=0, label_offset=0, max_seeds=None,
-                 train_priority=True):
+                 train_priority=True, sharded_blocks_per_sm=5):
         if len(fanouts) != 2 or len(model.layers) != 2:
             raise ValueError("PipelinedSageTrainer: 2-layer models / two fanouts")
         if (table is None) == (sharded is None):
@@ -88,6 +88,7 @@ class PipelinedSageTrainer:
         self.label_offset = int(label_offset)
         self._precision = precision
         self._train_priority = bool(train_priority)
+        self._sharded_bps = int(sharded_blocks_per_sm) if sharded_blocks_per_sm else 0
         dev = labels.device
         src = table if table is not None else sharded.table
         self._tdtype = src.dtype
@@ -217,6 +218,14 @@ class PipelinedSageTrainer:
         self._rng_off.copy_(keep[1])
         self.loss_sum.zero_()
         self._side = torch.cuda.Stream()
+        # The sharded aggregation of the produce branch sits on NVLink round trips while holding registers: at full
+        # residency it takes ~94 % of an SM's register file and the training branch's CTAs cannot start until it drains.
+        # Inside the step graph it is therefore captured with its residency capped at 5 blocks (10 warps) per SM — still
+        # ~6 MB in flight per GPU, three times what NVLink needs (8 GPUs, heaviest halo load: 0.488 -> 0.462 ms per step
+        # together with the stream priority below; either alone: 0.473 / 0.490; tools/ab_train_priority.py).
+        bps_prev = K.get_option("rows_sharded_bps")
+        if self.sharded is not None and self._sharded_bps:
+            K.set_option("rows_sharded_bps", self._sharded_bps)
         # the training branch is the critical path of a step (its last kernels are the all-reduce and Adam): it is captured
         # on a HIGH-priority stream, so that when both branches have blocks waiting the SMs go to the training kernels and
         # the produce branch (whose sharded aggregation holds SMs while its loads cross NVLink) fills what is left
@@ -232,6 +241,7 @@ class PipelinedSageTrainer:
                 self._train(self.slots[k])                    # ... while step i trains
                 cur.wait_stream(self._side)
             self.graphs.append(g)
+        K.set_option("rows_sharded_bps", bps_prev if bps_prev else None)
         self._prologue = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._prologue):
             self._produce(self.slots[0])

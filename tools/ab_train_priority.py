@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B of the pipelined trainer's stream priorities on the papers100M-shaped uniform control graph (the heaviest halo
-load): ms per step with the training branch captured on a high-priority stream vs default priorities.
+"""A/B of the pipelined trainer's overlap knobs on the papers100M-shaped uniform control graph (the heaviest halo
+load): ms per step with the training branch captured on a high-priority stream vs default priorities, and with the
+sharded aggregation's residency capped (option rows_sharded_bps).
   python tools/ab_train_priority.py            (1 GPU)
   torchrun --nproc-per-node N tools/ab_train_priority.py"""
 import json
@@ -49,15 +50,19 @@ def log(msg):
 
 
 log("setup done")
-for tag, prio in (("default_priorities", False), ("train_branch_high_priority", True), ("default_priorities_again", False),
-                  ("train_branch_high_priority_again", True)):
+from dgll_b200 import kernels as K  # noqa: E402
+
+VARIANTS = [("prio_base", True, None), ("prio_bps8", True, "8"), ("noprio_base", False, None), ("noprio_bps8", False, "8"),
+            ("noprio_bps5", False, "5"), ("noprio_bps12", False, "12"), ("prio_bps5", True, "5")]
+for tag, prio, bps in VARIANTS:
     log("variant " + tag)
     sharded = P.PeerShardedTable(N, table)
     torch.manual_seed(0)
     model = dnn.GraphSAGE(F, HIDDEN, C, 2, torch.relu, 0.0).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=0.003, fused=True, capturable=True)
     tr = PL.PipelinedSageTrainer(model, opt, labels, rp, col, F, sharded=sharded, batch_size=BATCH, fanouts=FANOUTS,
-                                 precision="tf32", rng_seed=11, label_offset=lo, max_seeds=per_rank, train_priority=prio)
+                                 precision="tf32", rng_seed=11, label_offset=lo, max_seeds=per_rank, train_priority=prio,
+                                 sharded_blocks_per_sm=int(bps) if bps else 0)
     tr.set_seeds(seeds)
     tr.capture()
     log("captured")
