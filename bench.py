@@ -734,7 +734,7 @@ def main():
     e2e_mode = "eager, double-buffered copy stream"
     graphs = None
     try:
-        side = torch.cuda.Stream(device=dev)
+        side, side2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         graphs = []
         torch.cuda.synchronize()
         for i in range(N_BATCHES):
@@ -742,6 +742,7 @@ def main():
             with torch.cuda.graph(gph):
                 cur = torch.cuda.current_stream()
                 side.wait_stream(cur)
+                side2.wait_stream(cur)
                 nb = (i + 1) % N_BATCHES
                 pb = (i - 1) % N_BATCHES
                 with torch.cuda.stream(side):
@@ -749,12 +750,17 @@ def main():
                     out_host[pb % 2][:batches[pb]["n_dst1"]].copy_(batches[pb]["agg1"], non_blocking=True)
                 bt, offs = batches[i], host[i][1]
                 v = [dev_buf[i % 2][o:o + m] for (o, m) in offs]
+                # the three kernels of a mini-batch do not depend on each other (layer 1 aggregates the given hidden
+                # table): the dst-row gather and the layer-1 aggregation run on a branch beside the layer-0 aggregation
+                with torch.cuda.stream(side2):
+                    K.gather_rows(table, v[2], out=bt["self0"])
+                    K.spmm_csr(v[3], v[4], bt["h1"], reduce="mean", out=bt["agg1"])
                 K.spmm_csr(v[0], v[1], view, reduce="mean", out=bt["agg0"])
-                K.gather_rows(table, v[2], out=bt["self0"])
-                K.spmm_csr(v[3], v[4], bt["h1"], reduce="mean", out=bt["agg1"])
+                cur.wait_stream(side2)
                 cur.wait_stream(side)
             graphs.append(gph)
-        e2e_mode = "CUDA graph per mini-batch (3 kernels || D2H of the previous result + H2D of the next batch)"
+        e2e_mode = ("CUDA graph per mini-batch ({layer-0 aggregation} || {dst-row gather, layer-1 aggregation} || "
+                    "{D2H of the previous result, H2D of the next batch})")
     except Exception as ex:  # capture unsupported: keep the eager pipeline
         graphs = None
         e2e_mode += " (graph capture failed: %s)" % type(ex).__name__
