@@ -798,6 +798,24 @@ def main():
         ref_out = K.spmm_csr(batches[last]["rp1"], batches[last]["col1"], batches[last]["h1"], reduce="mean")
         torch.cuda.synchronize()
         assert torch.equal(out_host[(args.steps - 1) % 2][:batches[last]["n_dst1"]].to(dev), ref_out), "e2e graph result"
+    # the same step as a BLOCKING call (what a caller without a pipeline sees): H2D of this batch's blocks, the three kernels,
+    # D2H of the result, host synchronisation — every step, nothing overlapped
+    blk_steps = min(args.steps, 200)
+    torch.cuda.synchronize()
+    t_blk = time.perf_counter()
+    for s_ in range(blk_steps):
+        i_ = s_ % N_BATCHES
+        hbuf, offs = host[i_]
+        bt = batches[i_]
+        dev_buf[0][:hbuf.numel()].copy_(hbuf, non_blocking=True)
+        v = [dev_buf[0][o:o + m] for (o, m) in offs]
+        K.spmm_csr(v[0], v[1], view, reduce="mean", out=bt["agg0"])
+        K.gather_rows(table, v[2], out=bt["self0"])
+        K.spmm_csr(v[3], v[4], bt["h1"], reduce="mean", out=bt["agg1"])
+        out_host[0][:bt["n_dst1"]].copy_(bt["agg1"], non_blocking=True)
+        torch.cuda.synchronize()
+    blk_ms = (time.perf_counter() - t_blk) * 1e3 / blk_steps
+    blk_bytes = sum(batches[s_ % N_BATCHES]["bytes"] for s_ in range(blk_steps)) / blk_steps
     clk = clocks.stop() if rank == 0 else None
     del graphs
 
@@ -908,7 +926,10 @@ def main():
                      "note": "frac counts every edge's full source row (SURVEY §8 d); dram_frac counts the bytes DRAM "
                              "actually moved — repeated source rows of a mini-batch are served by L2"},
         "e2e": {"value": e2e_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / args.steps,
-                "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode},
+                "d2h_bytes_per_step": d2h / args.steps, "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode,
+                "blocking_call": {"value": blk_bytes / (blk_ms * 1e-3) / 1e9, "ms_per_step": blk_ms, "steps": blk_steps,
+                                  "how": "per step: H2D of the batch's blocks, three kernels, D2H of the result, host "
+                                         "synchronisation; wall clock, nothing overlapped (rank 0)"}},
         "gpu_launches": launches, "clocks": clk, "gpu_baseline": gpu_baseline, "bf16_table": bf16,
         "epoch": epoch, "partitioned": partitioned, "setup_s": round(setup_s, 1),
     }
