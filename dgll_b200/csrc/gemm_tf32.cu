@@ -305,6 +305,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// v - trunc_tf32(v): what the tensor core drops when it reads the fp32 word v as tf32 (0 for Inf / NaN, which stay in hi)
+__device__ __forceinline__ float tf32_lo(float v) {
+    const float d = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    return (fabsf(v) <= 3.4028234664e38f) ? d : 0.f;
+}
+
 template <bool A_MN, bool B_MN, int BNP, bool X3>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -571,20 +577,18 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     float4* lo = hi + nv;
 #pragma unroll 4
                     for (int i = ct; i < nv; i += 128) {
+                        // The tensor core reads an fp32 word as tf32 by IGNORING its low 13 mantissa bits, so the landed word
+                        // itself serves as hi = trunc_tf32(v); only lo = rn_tf32(v - hi) has to be written (the stage is
+                        // shared-memory-bandwidth bound: TMA 32 KB in, the MMAs read 96 KB, the converters read 32 KB and, with
+                        // hi left in place, write 32 KB instead of 64 KB; ncu profiles/r02_gemm_x3.txt).  lo is rounded HERE
+                        // because the tensor core would truncate it too.
                         const float4 v = hi[i];
-                        float4 h, l;
+                        float4 l;
                         uint32_t u;
-                        // hi = rn_tf32(v); lo = rn_tf32(v - hi): lo is rounded HERE (to nearest) because the tensor core
-                        // would truncate it — a bias that grows linearly with K (first version: 4.3e-6 at K = 602)
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x - h.x)); l.x = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y - h.y)); l.y = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z - h.z)); l.z = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u);
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w - h.w)); l.w = __uint_as_float(u);
-                        hi[i] = h;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(tf32_lo(v.x))); l.x = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(tf32_lo(v.y))); l.y = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(tf32_lo(v.z))); l.z = __uint_as_float(u);
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(tf32_lo(v.w))); l.w = __uint_as_float(u);
                         lo[i] = l;
                     }
                 }
