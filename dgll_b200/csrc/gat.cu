@@ -784,20 +784,12 @@ gat_bwd_prep_kernel(const GatBwdParams p, float4* __restrict__ stats) {
 // stall on the first use of a loaded row.  Now: head masks are hoisted out of the edge loop (FFMA instead of
 // ISETP+FSEL), the scoring lane computes the row's byte offset once, the chunk's first P rows are requested BEFORE the
 // scores are computed, and nothing is zero-filled (short groups are skipped by warp-uniform branches).
-template <int NV, int P>
-__global__ void __launch_bounds__(32, 16)
-gat_backward_fused_kernel(const GatBwdParams p, const float4* __restrict__ stats, float* __restrict__ dz_ws) {
+template <int NV, bool HEAVY, int P>
+__device__ __forceinline__ void gat_backward_fused_body(const GatBwdParams& p, const float4* __restrict__ stats,
+                                                        float* __restrict__ dz_ws, const long long wid, long long* s_off,
+                                                        float (*s_a)[4], float2 (*s_bc)[4], float (*s_dz)[4]) {
     static_assert(32 % P == 0, "window depth must divide the 32-edge chunk");
-    __shared__ long long s_off[32];
-    __shared__ float s_a[32][4];
-    __shared__ float2 s_bc[32][4];
-    __shared__ __align__(16) float s_dz[32][4];
     const int lane = threadIdx.x;
-    // ONE launch: blocks [0, t_n_items) take the plan items of the long rows (they start first), the rest one row each —
-    // the short rows' dependent start-up round trips then overlap the long rows' streaming instead of following it
-    // (as two launches: 14.8 ms at 60 % DRAM, then 18.2 ms at 39 %; profiles/r02_gat_bwd_fused.txt)
-    const bool HEAVY = blockIdx.x < p.t_n_items;
-    const long long wid = HEAVY ? blockIdx.x : blockIdx.x - p.t_n_items;
     const int H = p.heads, FD = p.heads * p.D;
     long long row, beg, end;
     if (HEAVY) {
@@ -970,6 +962,23 @@ gat_backward_fused_kernel(const GatBwdParams p, const float4* __restrict__ stats
             stg_cs_f4(p.d_Wh + row * p.ldd + c0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
         }
     }
+}
+
+// ONE launch: blocks [0, t_n_items) take the plan items of the long rows (they start first), the rest one row each — the
+// short rows' dependent start-up round trips then overlap the long rows' streaming instead of following it (as two
+// launches: 14.8 ms at 60 % DRAM, then 18.2 ms at 39 %; profiles/r02_gat_bwd_fused_v2.txt).  Both bodies stay
+// compile-time specialised.
+template <int NV, int P>
+__global__ void __launch_bounds__(32, 16)
+gat_backward_fused_kernel(const GatBwdParams p, const float4* __restrict__ stats, float* __restrict__ dz_ws) {
+    __shared__ long long s_off[32];
+    __shared__ float s_a[32][4];
+    __shared__ float2 s_bc[32][4];
+    __shared__ __align__(16) float s_dz[32][4];
+    if (static_cast<long long>(blockIdx.x) < p.t_n_items)
+        gat_backward_fused_body<NV, true, P>(p, stats, dz_ws, blockIdx.x, s_off, s_a, s_bc, s_dz);
+    else
+        gat_backward_fused_body<NV, false, P>(p, stats, dz_ws, static_cast<long long>(blockIdx.x) - p.t_n_items, s_off, s_a, s_bc, s_dz);
 }
 
 // d_el_i = sum of dz over forward row i (dz_ws is [nnz, heads], CSR edge order): warp per row / per plan item
