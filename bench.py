@@ -734,6 +734,7 @@ def main():
     e2e_mode = "eager, double-buffered copy stream"
     graphs = None
     try:
+        # (a high-priority branch for the two short kernels made the step slower: 0.107 -> 0.118 ms)
         side, side2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         graphs = []
         torch.cuda.synchronize()
