@@ -64,3 +64,33 @@ def test_cpu_tensor_raises():
     x = torch.ones(1, 4)
     with pytest.raises(RuntimeError):
         K.spmm_csr(rp, col, x)
+
+
+def test_option_table_round_trip(built_lib):
+    """dgllb_set_option / dgllb_get_option need no device: every documented option is known, word values map to their
+    codes, numbers round-trip, ``None`` restores the default, unknown names and bad values are rejected with a message."""
+    from dgll_b200 import _lib
+    words = {"spmm_kernel": {"auto": 0, "rowsplit": 1, "stream": 2, "wholerow": 3},
+             "gat_kernel": {"auto": 0, "group": 1, "row": 2},
+             "gat_bwd_kernel": {"auto": 0, "twopass": 1, "fused": 2}}
+    numeric = ["spmm_tb", "rows_tb", "rows_ns", "rows_d", "rows_stream", "rows_sharded_bps", "gat_row_warps", "gat_bwd_tb",
+               "gat_bwd_depth", "bin_tb", "gemm_kernel", "nvtx"]
+    try:
+        for name, table in words.items():
+            for w, code in table.items():
+                _lib.set_option(name, w)
+                assert _lib.get_option(name) == code
+            _lib.set_option(name, None)
+            assert _lib.get_option(name) == 0
+        for name in numeric:
+            _lib.set_option(name, 7)
+            assert _lib.get_option(name) == 7
+            _lib.set_option(name, None)
+            assert _lib.get_option(name) == 0
+        with pytest.raises(RuntimeError):
+            _lib.set_option("no_such_option", "1")
+        with pytest.raises(RuntimeError):
+            _lib.set_option("spmm_kernel", "bogus")
+    finally:
+        for name in list(words) + numeric:
+            _lib.set_option(name, None)
