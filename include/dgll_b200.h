@@ -69,7 +69,13 @@ int64_t dgllb_launch_count(void);
  * environment variable DGLLB_<NAME> (read ONCE per process) and is changed afterwards only here; no launch path calls
  * getenv().  `value` is a decimal integer or one of the option's words; NULL / "" / "auto" = library default.
  *   spmm_kernel  auto | rowsplit | stream | wholerow        gat_kernel  auto | group | row
- *   spmm_tb, rows_tb, rows_ns, rows_d, rows_stream (1 = off, n >= 2 = n rows per warp), gat_row_warps, gat_bwd_tb, bin_tb, gemm_kernel   integers (0 = default)
+ *   gat_bwd_kernel  auto | twopass | fused  (fused = the single pass over the transposed CSR, default where it applies)
+ *   spmm_tb, rows_tb, rows_ns, rows_d, rows_stream (1 = off, n >= 2 = n rows per warp), gat_row_warps, gat_bwd_tb,
+ *   gat_bwd_depth (gradient rows in flight per lane: 4 | 8), bin_tb                               integers (0 = default)
+ *   rows_sharded_bps  resident 64-thread blocks per SM of dgllb_spmm_csr_sharded (5..16; 0 = no limit) — a caller that
+ *                     runs it beside other work (the pipelined trainer) keeps it from filling the register file
+ *   gemm_kernel  3 = precision-2 one-tile-per-CTA kernel, 4 = precision-2 persistent kernel, 5 = precision 0 always on
+ *                the exact FMA kernel (0 = automatic choice)
  *   nvtx         1 = NVTX ranges around the entry points named like the reference's (FeatureCache/storage.py:164-206)
  */
 int dgllb_set_option(const char* name, const char* value);
