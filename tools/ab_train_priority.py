@@ -50,8 +50,6 @@ def log(msg):
 
 
 log("setup done")
-from dgll_b200 import kernels as K  # noqa: E402
-
 VARIANTS = [("prio_base", True, None), ("prio_bps8", True, "8"), ("noprio_base", False, None), ("noprio_bps8", False, "8"),
             ("noprio_bps5", False, "5"), ("noprio_bps12", False, "12"), ("prio_bps5", True, "5")]
 for tag, prio, bps in VARIANTS:
